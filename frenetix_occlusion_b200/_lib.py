@@ -1,0 +1,102 @@
+"""ctypes binding of ``libfo_b200.so`` (C ABI declared in ``include/fo_b200.h``).
+
+There is no CPU fallback: if the shared library has not been built (``python __graft_entry__.py``
+or ``make -C frenetix_occlusion_b200/csrc``) importing this module raises ``ImportError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfo_b200.so")
+
+FO_OK = 0
+FO_MAX_STATES = 128
+FO_SUMMARY_K = 10
+FO_PAIR_K = 12
+FO_STEP_K = 3
+
+# metric bits (FO_M_*), threshold bits (FO_T_*), kinds (FO_KIND_*), flags (FO_F_*)
+M_BITS = {"cp": 1 << 0, "dce": 1 << 1, "ttc": 1 << 2, "hr": 1 << 3, "be": 1 << 4, "ttce": 1 << 5, "wttc": 1 << 6}
+T_BITS = {"harm": 1 << 0, "risk": 1 << 1, "be": 1 << 2, "cp": 1 << 3, "ttc": 1 << 4, "dce": 1 << 5}
+KINDS = {"pedestrian": 0, "bicycle": 1, "car": 2, "truck": 3, "bus": 4, "motorcycle": 5, "priorityvehicle": 6,
+         "parkedvehicle": 7, "taxi": 8, "train": 9, "unknown": 10}
+F_BE_RANGE = 1 << 0
+
+SUMMARY_FIELDS = ("max_ego_risk_all", "max_obst_risk_all", "max_ego_harm_all", "max_obst_harm_all",
+                  "max_collision_probability_all", "max_obst_harm_with_cp_all", "min_dce", "wttc",
+                  "max_break_threat_number", "max_required_constant_deceleration")
+PAIR_FIELDS = ("dce", "time_dce", "max_ego_risk", "max_obst_risk", "max_obst_risk_index", "max_obst_harm_with_cp",
+               "max_ego_harm", "max_obst_harm", "max_collision_probability", "required_constant_deceleration",
+               "break_threat_number", "argmax_cp_index")
+
+
+class FoVehicle(C.Structure):
+    _fields_ = [("length", C.c_float), ("width", C.c_float), ("mass", C.c_float), ("wb_rear_axle", C.c_float),
+                ("a_max", C.c_float)]
+
+
+class FoHarmCoeffs(C.Structure):
+    _fields_ = [("rs_const", C.c_float), ("rs_speed", C.c_float), ("rs_side", C.c_float), ("rs_rear", C.c_float),
+                ("ia_const", C.c_float), ("ia_speed", C.c_float), ("ped_const", C.c_float), ("ped_speed", C.c_float)]
+
+
+class FoAgentsRaw(C.Structure):
+    _fields_ = [("n_agents", C.c_int32), ("t_stride", C.c_int32),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("yaw", C.c_void_p), ("v", C.c_void_p),
+                ("var_x", C.c_void_p), ("var_y", C.c_void_p), ("n_states", C.c_void_p), ("kind", C.c_void_p),
+                ("length", C.c_void_p), ("width", C.c_void_p), ("buf_length", C.c_void_p), ("buf_width", C.c_void_p)]
+
+
+class FoMetricArgs(C.Structure):
+    _fields_ = [("ego", C.c_void_p), ("n_traj", C.c_int32), ("n_states", C.c_int32),
+                ("agent_table", C.c_void_p), ("n_agents", C.c_int32), ("t_stride", C.c_int32),
+                ("vehicle", FoVehicle), ("harm", FoHarmCoeffs), ("dt", C.c_double),
+                ("metric_mask", C.c_uint32), ("threshold_mask", C.c_uint32),
+                ("thr_harm", C.c_double), ("thr_risk", C.c_double), ("thr_be", C.c_double),
+                ("thr_cp", C.c_double), ("thr_ttc", C.c_double), ("thr_dce", C.c_double),
+                ("valid", C.c_void_p), ("summary", C.c_void_p), ("flags", C.c_void_p),
+                ("pair", C.c_void_p), ("step", C.c_void_p)]
+
+
+# every symbol include/fo_b200.h declares: name -> (restype, argtypes)
+_PROTOS = {
+    "fo_agent_table_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "fo_agents_pack": (C.c_int, [C.POINTER(FoAgentsRaw), C.POINTER(FoVehicle), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fo_metric_bundle": (C.c_int, [C.POINTER(FoMetricArgs), C.c_void_p]),
+    "fo_metric_bundle_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(FoAgentsRaw),
+                                        C.POINTER(FoMetricArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),
+    "fo_launch_count": (C.c_uint64, []),
+    "fo_version": (C.c_int, []),
+    "fo_last_error": (C.c_char_p, []),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+
+class FoError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built -- run `python __graft_entry__.py` (or make -C "
+                          "frenetix_occlusion_b200/csrc); this package has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)        # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = ""):
+    if rc != FO_OK:
+        msg = lib.fo_last_error().decode("utf-8", "replace")
+        raise FoError(f"{what or 'libfo_b200'} failed with status {rc}: {msg}")

@@ -1,0 +1,169 @@
+/*
+ * fo_b200.h -- C ABI of the B200-native Frenetix-Occlusion assessment hot path (libfo_b200.so).
+ *
+ * Plain C: device/host pointers and sizes only, no torch / C++ types.  Every entry point returns
+ * FO_OK (0) or a negative FoStatus; nothing throws across the boundary; fo_last_error() gives the
+ * thread-local message of the last failure.  "dev" pointers are CUDA device pointers owned by the
+ * caller (they must stay alive until the stream work has completed); all device entry points are
+ * asynchronous on the given stream (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *
+ * The reference is pure Python and has no FFI; each entry point names the reference interface it
+ * replaces (paths relative to the reference repository root).  The Python host
+ * (frenetix_occlusion_b200/) binds these with ctypes, see INTEGRATION.md.
+ */
+#ifndef FO_B200_H
+#define FO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO_ABI_VERSION 1
+
+typedef enum FoStatus {
+  FO_OK = 0,
+  FO_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, unsupported shape */
+  FO_ERR_UNSUPPORTED = -2,   /* e.g. T > FO_MAX_STATES */
+  FO_ERR_CUDA = -3,          /* a CUDA runtime call failed (message in fo_last_error) */
+  FO_ERR_NO_DEVICE = -4
+} FoStatus;
+
+#define FO_MAX_STATES 128    /* states per trajectory / prediction (reference uses 31 and 51) */
+
+/* ---- metric activation bits: names of frenetix_occlusion/metrics/metric.py:109-117 ------------ */
+enum {
+  FO_M_CP = 1u << 0, FO_M_DCE = 1u << 1, FO_M_TTC = 1u << 2, FO_M_HR = 1u << 3,
+  FO_M_BE = 1u << 4, FO_M_TTCE = 1u << 5, FO_M_WTTC = 1u << 6
+};
+/* ---- armed-threshold bits: metric_thresholds of configurations/simulation/occlusion.yaml:20-28;
+ *      only these six are ever checked by the reference (metric.py:55-98) ---------------------- */
+enum {
+  FO_T_HARM = 1u << 0, FO_T_RISK = 1u << 1, FO_T_BE = 1u << 2, FO_T_CP = 1u << 3,
+  FO_T_TTC = 1u << 4, FO_T_DCE = 1u << 5
+};
+/* ---- agent kinds (commonroad ObstacleType values the reference can produce, agent.py:74-120,
+ *      harm_model.py:15-32,158-190) ------------------------------------------------------------- */
+enum {
+  FO_KIND_PEDESTRIAN = 0, FO_KIND_BICYCLE = 1, FO_KIND_CAR = 2, FO_KIND_TRUCK = 3,
+  FO_KIND_BUS = 4, FO_KIND_MOTORCYCLE = 5, FO_KIND_PRIORITY_VEHICLE = 6, FO_KIND_PARKED_VEHICLE = 7,
+  FO_KIND_TAXI = 8, FO_KIND_TRAIN = 9, FO_KIND_UNKNOWN = 10
+};
+
+/* per-trajectory flag bits written to FoMetricArgs.flags */
+enum {
+  FO_F_BE_RANGE = 1u << 0    /* reference raises ValueError here: re-timed path overruns the original
+                                (scipy interp1d bounds_error, metrics/be.py:117-124) */
+};
+
+/* Ego vehicle parameters: vehicle_params.{length,width,mass,wb_rear_axle,a_max}
+ * (collision_probability.py:35, harm_model.py:96-97, convert_dynamic_obstacle.py:60,78, be.py:56). */
+typedef struct FoVehicle {
+  float length, width, mass, wb_rear_axle, a_max;
+} FoVehicle;
+
+/* Logistic harm coefficients: frenetix_occlusion/config/harm_params.json keys
+ * log_reg.reduced_sym_angle_areas.{const,speed,side,rear}, log_reg.ignore_angle.{const,speed},
+ * pedestrian.{const,speed} (logistic_regression.py:35-48,71-73; harm_model.py:137-146). */
+typedef struct FoHarmCoeffs {
+  float rs_const, rs_speed, rs_side, rs_rear;
+  float ia_const, ia_speed;
+  float ped_const, ped_speed;
+} FoHarmCoeffs;
+
+/* Raw phantom-agent predictions, SoA, padded to t_stride states per agent: what
+ * FOAgentManager.predictions holds per prediction id (agent.py:420-424, 530-534) plus the owning
+ * agent's type and unbuffered shape (agent.py:213-217).  All pointers are device pointers. */
+typedef struct FoAgentsRaw {
+  int32_t n_agents;
+  int32_t t_stride;            /* padded row length (>= max n_states) */
+  const float *x, *y;          /* [A, t_stride] pos_list */
+  const float *yaw;            /* [A, t_stride] orientation_list */
+  const float *v;              /* [A, t_stride] v_list */
+  const float *var_x, *var_y;  /* [A, t_stride] diag(cov_list); both 0 -> 0.1 (collision_probability.py:85-87) */
+  const int32_t *n_states;     /* [A] len(pos_list) */
+  const int32_t *kind;         /* [A] FO_KIND_* */
+  const float *length, *width; /* [A] agent.shape (unbuffered) -> DCE / BE rectangles */
+  const float *buf_length, *buf_width; /* [A] prediction['shape'] (buffered) -> CP points, mass */
+} FoAgentsRaw;
+
+/* Number of bytes of device memory fo_agents_pack() needs for its packed table. */
+size_t fo_agent_table_bytes(int32_t n_agents, int32_t t_stride);
+
+/* Stage 2 -> stage 3 hand-over: derive per-state (cos,sin yaw, 1/(sqrt2 sigma)) and per-agent
+ * (protection class, mass split m_o/(m_e+m_o), half extents) quantities once per planning cycle.
+ * Replaces the per-trajectory re-derivation in harm_model.py:58-79 and
+ * convert_dynamic_obstacle.py:17-49. */
+int fo_agents_pack(const FoAgentsRaw *raw, const FoVehicle *vehicle, void *table_dev, size_t table_bytes,
+                   void *stream);
+
+#define FO_SUMMARY_K 10
+/* summary[n, :] = { max_ego_risk_all, max_obst_risk_all, max_ego_harm_all, max_obst_harm_all,
+ *                   max_collision_probability_all, max_obst_harm_with_cp_all   (hr.py:108-114),
+ *                   min over agents of dce [m]            (dce.py:52-99; +inf without agents),
+ *                   wttc [s]                              (wttc.py:32-42; +inf = no collision),
+ *                   max over agents of break_threat_number (be.py:56),
+ *                   max over agents of required_constant_deceleration (be.py:53) } */
+#define FO_PAIR_K 12
+/* pair[n, a, :] = { dce, time_dce, max_ego_risk, max_obst_risk, max_obst_risk_index,
+ *                   max_obst_harm_with_cp, max_ego_harm, max_obst_harm, max_collision_probability,
+ *                   required_constant_deceleration, break_threat_number, argmax_cp_index } */
+#define FO_STEP_K 3
+/* step[n, a, j, :] = { collision_probability[j] (CP of ego step j+1), ego_harm[j], obst_harm[j] },
+ *                    j in [0, T-1); harm entries are NaN for j >= min(T-1, n_states[a]). */
+
+typedef struct FoMetricArgs {
+  /* ---- inputs --------------------------------------------------------------------------------- */
+  const float *ego;        /* dev [N, T, 5] (x, y, theta, v, a): trajectory.cartesian.* of every sampled
+                              trajectory, rear-axle reference point */
+  int32_t n_traj;          /* N */
+  int32_t n_states;        /* T = len(trajectory.cartesian.x) */
+  const void *agent_table; /* dev, written by fo_agents_pack */
+  int32_t n_agents;        /* A (0 -> every trajectory valid, metric.py:44-45) */
+  int32_t t_stride;
+  FoVehicle vehicle;
+  FoHarmCoeffs harm;
+  double dt;               /* agent_manager.dt */
+  uint32_t metric_mask;    /* FO_M_* after dependency resolution (metric.py:125-147) */
+  uint32_t threshold_mask; /* FO_T_* for thresholds that are not null */
+  double thr_harm, thr_risk, thr_be, thr_cp, thr_ttc, thr_dce;  /* strict > / < as metric.py:55-98 */
+  /* ---- outputs (device; optional ones may be NULL) --------------------------------------------- */
+  uint8_t *valid;          /* [N] safety_check of Metric.evaluate_metrics */
+  float *summary;          /* [N, FO_SUMMARY_K] */
+  uint32_t *flags;         /* [N] FO_F_* */
+  float *pair;             /* [N, A, FO_PAIR_K] or NULL */
+  float *step;             /* [N, A, T-1, FO_STEP_K] or NULL */
+} FoMetricArgs;
+
+/* Stage 3, the dense core: every trajectory x every phantom prediction x every step.
+ * Replaces Metric.evaluate_metrics (metrics/metric.py:35-100) and everything it dispatches to
+ * (cp.py, dce.py, ttc.py, ttce.py, wttc.py, hr.py, be.py, metrics/utils/*.py) for a whole bundle. */
+int fo_metric_bundle(const FoMetricArgs *args, void *stream);
+
+/* Same computation driven from HOST buffers (pinned or pageable): copies ego / agents to the
+ * device, runs fo_agents_pack + fo_metric_bundle, copies valid/summary/flags back and synchronises.
+ * This is the call a non-torch embedder of the reference would make; device workspace is owned by
+ * the library and grown on demand (per calling thread). `agents` holds HOST pointers here;
+ * `out_pair` / `out_step` may be NULL. */
+int fo_metric_bundle_host(const float *ego_host, int32_t n_traj, int32_t n_states, const FoAgentsRaw *agents_host,
+                          const FoMetricArgs *params /* vehicle, harm, dt, masks, thresholds are read */,
+                          uint8_t *out_valid, float *out_summary, uint32_t *out_flags, float *out_pair,
+                          float *out_step);
+
+/* FP32 FMA-pipe probe used by bench.py to measure the roofline denominator on the box it runs on:
+ * runs `iters` dependent-chain FFMAs on every lane of a full-occupancy grid and returns elapsed
+ * milliseconds (CUDA events) in *ms and the flop count in *flops. */
+int fo_probe_fp32_peak(int32_t iters, float *ms, double *flops, void *stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t fo_launch_count(void);
+
+int fo_version(void);
+const char *fo_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FO_B200_H */

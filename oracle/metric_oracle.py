@@ -88,6 +88,7 @@ def collision_probability(case):
     L, W = case["vehicle"]["length"], case["vehicle"]["width"]
     cp = np.zeros((N, A, max(T - 1, 0)))
     inside = np.zeros((N, A, max(T - 1, 0)), dtype=bool)
+    gate_margin = np.full((N, A, max(T - 1, 0)), np.inf)   # |min distance - 5.0| (tie diagnostics)
     for a in range(A):
         nmax = min(T, Ta[a])          # i < len(mean_list)
         if nmax < 2:
@@ -116,7 +117,8 @@ def collision_probability(case):
         prob = (pr[..., 0] * pr[..., 1]).sum((1, 2)) / 3.0            # :115-122
         cp[:, a, i - 1] = np.where(gate, 0.0, prob)
         inside[:, a, i - 1] = ~gate
-    return cp, inside
+        gate_margin[:, a, i - 1] = np.abs(d.min(1) - 5.0)
+    return cp, inside, gate_margin
 
 
 def dce_metric(case):
@@ -271,8 +273,10 @@ def evaluate_bundle(case, want_detail: bool = True):
         return out
     Ta = np.array([len(np.asarray(a["yaw"])) for a in case["agents"]])
     if "cp" in order:
-        cp, inside = collision_probability(case)
+        cp, inside, gate_margin = collision_probability(case)
         out["cp"] = cp
+        if want_detail:
+            out["gate_margin"] = gate_margin
         out["gate_fraction"] = float(inside.mean()) if inside.size else 0.0
     if "dce" in order:
         dce, tdce, dist = dce_metric(case)

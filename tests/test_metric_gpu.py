@@ -1,0 +1,132 @@
+"""Parity of the CUDA dense metric core (through the C ABI) against the float64 oracle and the
+reference-generated golden vectors.  Needs a GPU: run with ``-m gpu`` on the B200 box."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_files
+from frenetix_occlusion_b200 import synthetic as S
+from oracle import metric_oracle as MO
+from oracle.compare import compare_results
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(rep, max_tie_rate=0.03):
+    assert not rep["fail"], "\n".join(rep["fail"])
+    n_ties = sum(rep["ties"].values())
+    assert n_ties <= max(3, max_tie_rate * rep["n_pairs"]), rep["ties"]
+
+
+@pytest.mark.parametrize("fname", golden_files("metric_"))
+def test_cuda_matches_oracle_on_golden_cases(fname, cuda_device):
+    case, reference, order = MO.load_case_json(os.path.join(GOLDEN, fname))
+    out = MO.evaluate_bundle(case)
+    res, eng = parity.run_gpu(case)
+    assert eng.order == order
+    _check(parity.compare_bundle(out, res, case))
+
+
+@pytest.mark.parametrize("fname", ["metric_kat_pedestrian.json", "metric_closed_form.json", "metric_ragged_lengths.json"])
+def test_cuda_matches_reference_dicts_directly(fname, cuda_device):
+    """The drop-in ``Metric.evaluate_metrics`` against the reference's own result dicts."""
+    from frenetix_occlusion_b200.metrics.metric import Metric
+    from oracle.ref_runner import TrajectoryStub
+    from oracle import ref_runner
+    import types
+    case, reference, order = MO.load_case_json(os.path.join(GOLDEN, fname))
+    am = _agent_manager_from_case(case)
+    vp = types.SimpleNamespace(**case["vehicle"])
+    metric = Metric({"activated_metrics": list(case["activated_metrics"]), "metric_thresholds": dict(case["thresholds"])},
+                    vp, am)
+    assert list(metric.metrics.keys()) == order
+    for n, ref in enumerate(reference):
+        if ref["safety_check"] is None:
+            with pytest.raises(ValueError):
+                metric.evaluate_metrics(TrajectoryStub(case["ego"][n]))
+            continue
+        results, ok = metric.evaluate_metrics(TrajectoryStub(case["ego"][n]))
+        problems = compare_results(ref["results"], results, rtol=1e-4, atol=2e-6)
+        assert not problems, f"{fname}[{n}]:\n" + "\n".join(problems[:10])
+        assert ok == ref["safety_check"]
+
+
+def _agent_manager_from_case(case):
+    import types
+    am = types.SimpleNamespace(dt=case["dt"], visualization=None, phantom_agents=[], predictions={})
+    for k, ag in enumerate(case["agents"]):
+        agent = types.SimpleNamespace(agent_id=10000 + k, agent_type=ag["agent_type"],
+                                      shape=types.SimpleNamespace(length=ag["length"], width=ag["width"]))
+        am.phantom_agents.append(agent)
+        var = np.asarray(ag["var"])
+        am.predictions[int(str(10000 + k) + "0")] = {
+            "orientation_list": np.asarray(ag["yaw"]), "v_list": np.asarray(ag["v"]),
+            "pos_list": np.asarray(ag["pos"]).reshape(-1, 2),
+            "shape": {"length": ag["buf_length"], "width": ag["buf_width"]},
+            "cov_list": np.array([[[v, 0.0], [0.0, v]] for v in var])}
+    am.agent_by_prediction_id = lambda pid: next(a for a in am.phantom_agents if a.agent_id == int(str(pid)[:5]))
+    return am
+
+
+@pytest.mark.parametrize("seed,n,a,t", [(1, 64, 16, 31), (2, 50, 12, 51), (3, 200, 32, 31), (4, 33, 5, 2), (5, 40, 9, 97)])
+def test_cuda_matches_oracle_on_random_bundles(seed, n, a, t, cuda_device):
+    case = S.make_case(n, a, t, seed=seed)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case)
+    _check(parity.compare_bundle(out, res, case))
+
+
+def test_latency_config_parity(cuda_device):
+    """BASELINE config C-lat (1k x 32 x 30 steps), all seven metrics, full detail compared."""
+    case = S.make_case(1000, 32, 31)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case)
+    rep = parity.compare_bundle(out, res, case)
+    _check(rep)
+
+
+def test_summary_only_equals_detail_path(cuda_device):
+    """Summary-only launch (the bench path) must give the same valid/summary as the detail launch."""
+    case = S.make_case(3000, 48, 51, seed=9)
+    res_d, _ = parity.run_gpu(case, want_pair=True, want_step=True)
+    res_s, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    assert np.array_equal(res_d["valid"], res_s["valid"])
+    assert np.array_equal(res_d["flags"], res_s["flags"])
+    assert np.array_equal(res_d["summary"], res_s["summary"], equal_nan=True)
+    # and the summary is the reduction of the per-pair detail
+    p = res_d["pair"]
+    ok = (res_d["flags"] & 1) == 0
+    assert np.array_equal(res_d["summary"][:, 6], p[..., 0].min(1))
+    assert np.array_equal(res_d["summary"][ok, 8], p[ok][..., 10].max(1))
+    for col_s, col_p in ((0, 2), (1, 3), (2, 6), (3, 7), (4, 8), (5, 5)):
+        assert np.array_equal(res_d["summary"][:, col_s], p[..., col_p].max(1))
+
+
+def test_edge_cases(cuda_device):
+    # no agents -> every trajectory valid (metric.py:44-45)
+    case = S.make_case(10, 0, 31)
+    res, _ = parity.run_gpu(case)
+    assert res["valid"].all()
+    # empty bundle
+    case = S.make_case(0, 4, 31)
+    res, _ = parity.run_gpu(case)
+    assert res["valid"].shape == (0,)
+    # thresholds: translation invariance through the origin shift
+    case = S.make_case(40, 8, 31, seed=21)
+    res0, _ = parity.run_gpu(case)
+    import copy
+    from frenetix_occlusion_b200.engine import AgentSet, MetricEngine
+    import torch
+    shifted = copy.deepcopy(case)
+    off = np.array([4096.0, -2048.0])     # exactly representable shift
+    shifted["ego"][..., 0:2] += off
+    for ag in shifted["agents"]:
+        ag["pos"] = np.asarray(ag["pos"]) + off
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"])
+    eng.set_agents(AgentSet.from_case(shifted["agents"]), origin=off)
+    r = eng.assess(shifted["ego"])
+    torch.cuda.synchronize()
+    assert np.array_equal(r.valid.cpu().numpy(), res0["valid"])
+    assert np.array_equal(r.summary.cpu().numpy(), res0["summary"], equal_nan=True)
