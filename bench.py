@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the per-planning-step assessment hot path (BASELINE.json metric:
+trajectory x agent x step evaluations / s; p50 per-planning-step latency).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c-sweep|c-lat]
+
+One "step" = one pass of the dense metric core over the whole synthetic sweep bundle
+(C-sweep: 1,000,000 trajectories x 256 phantom agents x 50 steps, all seven metrics), split by
+trajectory over the ranks (strong scaling, total work fixed) followed by ONE all-gather of the
+per-trajectory result vectors when N > 1.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from frenetix_occlusion_b200 import synthetic as S  # noqa: E402
+
+METRIC = "traj_agent_step_evals_per_s"
+UNIT = "evals/s"
+CHUNK = 125_000          # trajectories per generation chunk (8 chunks = the 1 M sweep)
+
+# ALGORITHMIC work per evaluation (DESIGN.md "Roofline"):
+#   F(g, c) = 300 + 1050*g flop per (trajectory, agent, step) evaluation, g = fraction of evaluations
+#   inside the 5 m CP gate; plus BE: per colliding pair ~6 bisection probes x T steps x 60 flop.
+F_BASE, F_CP, F_BE_STEP = 300.0, 1050.0, 60.0
+FP32_PEAK_FALLBACK_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz (only if the probe fails)
+
+
+def workload(name):
+    if name == "c-lat":
+        return dict(S.C_LAT)
+    return dict(S.C_SWEEP)
+
+
+def gen_ego(n_traj, n_states, first_chunk):
+    """Deterministic global bundle: chunk k of CHUNK trajectories is seeded with SEED + 100 + k."""
+    out = np.empty((n_traj, n_states, 5), dtype=np.float32)
+    done, k = 0, first_chunk
+    while done < n_traj:
+        m = min(CHUNK, n_traj - done)
+        out[done:done + m] = S.ego_bundle(m, n_states, seed=S.SEED + 100 + k).astype(np.float32)
+        done += m
+        k += 1
+    return out
+
+
+def make_case(wl, n_traj, first_chunk=0):
+    return {"dt": 0.1, "vehicle": {k: float(S._f32(v)) for k, v in S.VEHICLE.items()},
+            "ego": gen_ego(n_traj, wl["n_states"], first_chunk),
+            "agents": S.agent_table(wl["n_agents"], wl["n_states"], seed=S.SEED + 1),
+            "activated_metrics": list(S.ALL_METRICS), "thresholds": dict(S.DEFAULT_THRESHOLDS)}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _oracle_chunk(args):
+    case, lo, hi = args
+    from oracle import metric_oracle as MO
+    sub = dict(case)
+    sub["ego"] = np.asarray(case["ego"][lo:hi], dtype=np.float64)
+    out = MO.evaluate_bundle(sub, want_detail=False)
+    return int(out["valid"].sum())
+
+
+def cpu_oracle_throughput(wl, n_traj_sample, cores, steps=1, warmup=0):
+    """Times the CPU restatement of the path (oracle B, float64 numpy -- the reference itself needs
+    shapely/commonroad/frenetix and cannot be installed here) on ``cores`` processes."""
+    import multiprocessing as mp
+    case = make_case(wl, n_traj_sample)
+    bounds = np.linspace(0, n_traj_sample, cores + 1).astype(int)
+    jobs = [(case, int(bounds[i]), int(bounds[i + 1])) for i in range(cores) if bounds[i + 1] > bounds[i]]
+    evals = n_traj_sample * wl["n_agents"] * (wl["n_states"] - 1)
+    times = []
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_chunk, jobs)
+            t1 = time.perf_counter()
+            if it >= warmup:
+                times.append(t1 - t0)
+    sec = float(np.mean(times))
+    return evals / sec, sec, evals
+
+
+def run_reference(args):
+    """--impl reference: the path's CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload)
+    cores = os.cpu_count() or 1
+    n_sample = min(wl["n_traj"], 64 * cores if wl["n_agents"] >= 128 else 1000)
+    value, sec, evals = cpu_oracle_throughput(wl, n_sample, cores, steps=args.steps, warmup=args.warmup)
+    sample = (f"{n_sample} of {wl['n_traj']} trajectories x {wl['n_agents']} agents x {wl['n_states'] - 1} steps per step, "
+              f"oracle B (vectorised float64 numpy port of the reference metrics) on {cores} processes")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_traj": wl["n_traj"], "n_agents": wl["n_agents"],
+                       "n_steps": wl["n_states"] - 1, "metrics": "all7", "sample_traj": n_sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from frenetix_occlusion_b200 import _lib as L
+    from frenetix_occlusion_b200.engine import AgentSet, MetricEngine, BundleResult
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workload(args.workload)
+    N_total, A, T = wl["n_traj"], wl["n_agents"], wl["n_states"]
+    # contiguous trajectory shard of this rank (strong scaling)
+    per = (N_total + world - 1) // world
+    lo, hi = rank * per, min(N_total, (rank + 1) * per)
+    n_local = hi - lo
+    assert lo % CHUNK == 0 or world == 1 or N_total < CHUNK, "shards must align with generation chunks"
+    case = make_case(wl, n_local, first_chunk=lo // CHUNK)
+    ego_host = torch.from_numpy(case["ego"]).pin_memory()
+
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"], device=dev)
+    eng.set_agents(AgentSet.from_case(case["agents"]))
+    ego_dev = ego_host.to(dev)
+    out = BundleResult(torch.empty(n_local, dtype=torch.uint8, device=dev),
+                       torch.empty((n_local, L.FO_SUMMARY_K), dtype=torch.float32, device=dev),
+                       torch.empty(n_local, dtype=torch.int32, device=dev))
+    if world > 1:
+        g_valid = torch.empty(per * world, dtype=torch.uint8, device=dev)
+        g_summary = torch.empty((per * world, L.FO_SUMMARY_K), dtype=torch.float32, device=dev)
+        pad_valid = torch.zeros(per, dtype=torch.uint8, device=dev)
+        pad_summary = torch.zeros((per, L.FO_SUMMARY_K), dtype=torch.float32, device=dev)
+    host_valid = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    host_summary = torch.empty((n_local, L.FO_SUMMARY_K), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        eng.assess(ego_dev, out=out)
+        if world > 1:   # the single collective of the path: all-gather of the result vectors
+            pad_valid[:n_local].copy_(out.valid)
+            pad_summary[:n_local].copy_(out.summary)
+            dist.all_gather_into_tensor(g_valid, pad_valid)
+            dist.all_gather_into_tensor(g_summary, pad_summary)
+
+    def step_e2e():
+        d = ego_host.to(dev, non_blocking=True)          # H2D of this step's inputs from pinned memory
+        eng.assess(d, out=out)
+        host_valid.copy_(out.valid, non_blocking=True)   # D2H of the step's result
+        host_summary.copy_(out.summary, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False, per_step_events=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler is not None and sampler.ok:
+            sampler.start()
+        launches0 = L.lib.fo_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern = []
+        e0.record()
+        for _ in range(steps):
+            if per_step_events:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eng.assess(ego_dev, out=out)
+                b.record()
+                kern.append((a, b))
+                if world > 1:
+                    pad_valid[:n_local].copy_(out.valid)
+                    pad_summary[:n_local].copy_(out.summary)
+                    dist.all_gather_into_tensor(g_valid, pad_valid)
+                    dist.all_gather_into_tensor(g_summary, pad_summary)
+            else:
+                fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.lib.fo_launch_count() - launches0
+        clocks = sampler.stop() if sampler is not None else None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        kern_ms = [a.elapsed_time(b) for a, b in kern]
+        return ms, launches, clocks, kern_ms
+
+    evals_total = N_total * A * (T - 1)
+    ms, launches, clocks, kern_ms = timed(step_resident, args.steps, args.warmup, sample_clocks=True, per_step_events=True)
+    value = evals_total * args.steps / (ms * 1e-3)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    e2e_value = evals_total * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- workload statistics for the algorithmic flop count (sample of the same bundle, on the GPU) ----
+    samp = min(n_local, 20000)
+    r = eng.assess(ego_dev[:samp], want_pair=True, want_step=True)
+    torch.cuda.synchronize()
+    g_frac = float((r.step[..., 0] > 0).float().mean().item()) if T > 1 else 0.0   # lower bound of the gate fraction
+    be_pairs = float((r.pair[..., 9] > 0).float().mean().item())
+    flop_per_eval = F_BASE + F_CP * g_frac + be_pairs * 6 * T * F_BE_STEP / (T - 1)
+    del r
+
+    # ---- FP32 peak of THIS box (own FMA probe), HBM peak from the driver-written file ------------------
+    import ctypes as C
+    ms_p, fl_p = C.c_float(), C.c_double()
+    peak_tflops, peak_src = FP32_PEAK_FALLBACK_TFLOPS, "fallback (148 SM x 128 lanes x 2 x 1.965 GHz)"
+    if L.lib.fo_probe_fp32_peak(200000, C.byref(ms_p), C.byref(fl_p), None) == 0 and ms_p.value > 0:
+        peak_tflops, peak_src = fl_p.value / (ms_p.value * 1e-3) / 1e12, "measured: fo_probe_fp32_peak FFMA loop on this GPU"
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+
+    k_ms = float(np.mean(kern_ms)) if kern_ms else ms / args.steps
+    evals_local = n_local * A * (T - 1)
+    achieved_tflops = evals_local * flop_per_eval / (k_ms * 1e-3) / 1e12
+    alg_bytes = n_local * (T * 5 * 4 + 1 + 4 + 4 * L.FO_SUMMARY_K) + A * T * 32
+    roofline = {"bound": "fp32", "kernel": "fo_metric_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
+                "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "peak_source": peak_src,
+                "kernel_ms": k_ms, "flop_per_eval": flop_per_eval, "gate_fraction": g_frac, "be_pair_fraction": be_pairs,
+                "traffic": None,
+                "hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "peak_source": hbm_src},
+                "note": "reduced-output kernel is FP32/SFU-bound by construction (SURVEY.md 8d): HBM traffic is per "
+                        "trajectory, arithmetic per trajectory x agent x step"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = min(N_total, 48 * cores if A >= 128 else 1000)
+        v, sec, _ = cpu_oracle_throughput(wl, n_sample, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_sample} trajectories x {A} agents x {T - 1} steps, oracle B (float64 numpy port of the "
+                         f"reference metrics) on {cores} processes, {sec:.1f} s"}
+
+    # ---- p50 latency of the per-planning-step case (C-lat, device resident, one launch) -----------------
+    lat = None
+    if not args.no_latency:
+        lc = make_case(workload("c-lat"), 1000)
+        eng_l = MetricEngine(lc["vehicle"], lc["dt"], lc["activated_metrics"], lc["thresholds"], device=dev)
+        eng_l.set_agents(AgentSet.from_case(lc["agents"]))
+        ego_l = torch.from_numpy(lc["ego"]).to(dev)
+        out_l = eng_l.assess(ego_l)
+        for _ in range(50):
+            eng_l.assess(ego_l, out=out_l)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(1000):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng_l.assess(ego_l, out=out_l)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        lat = {"workload": "C-lat 1000x32x30 all7 device-resident", "p50_us": float(np.percentile(ts, 50)),
+               "p95_us": float(np.percentile(ts, 95)), "iters": 1000}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_traj": N_total, "n_agents": A, "n_steps": T - 1, "metrics": "all7",
+                       "parallelism": f"traj-shard x{world} + 1 all_gather" if world > 1 else "single GPU",
+                       "l2": "inputs (1.02 GB bundle) larger than L2, no flush needed" if N_total * T * 20 > 2.5e8
+                             else "inputs smaller than L2 (latency case, resident by design)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * T * 5 * 4) * world,
+                    "d2h_bytes_per_step": int(n_local * (1 + 4 * L.FO_SUMMARY_K)) * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "latency": lat}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c-sweep", choices=["c-sweep", "c-lat"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,7 +169,7 @@ __device__ float be_bisect(const MetricKArgs& k, const EgoState (&e)[NP], float 
           float dy = (s0.y - yn) - k.wb * sn;
           float rx = fmaf(dx, cn, dy * sn), ry = fmaf(dy, cn, -dx * sn);
           float c = fmaf(cn, s0.z, sn * s0.w), s = fmaf(s0.w, cn, -s0.z * sn);
-          hit = obb_hit(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw);
+          hit |= obb_hit(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw);
         }
       }
     }
@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
             }
             carry += __shfl_sync(kFull, sc, 31);
           }
-          float am = -__uint_as_float(__reduce_max_sync(kFull, __float_as_uint(-amin)));  // amin <= 0
-          be_lo0 = rintf(fabsf(am) * 100.0f) / 100.0f;
+          float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));  // |min(min a, 0)|
+          be_lo0 = rintf(am * 100.0f) / 100.0f;
           __syncwarp();
           be_ready = true;
         }
