@@ -21,8 +21,11 @@ void count_launch(uint64_t n = 1);
   } while (0)
 
 // ---- packed agent table (written by fo_agents_pack, read by the metric kernels) ----------------
-// [ float4 s0[A*Tp] | float4 s1[A*Tp] | AgentParams prm[A] ]
-//   s0 = (px, py, cos yaw, sin yaw)          s1 = (yaw, v, 1/(sqrt2 sigma_x), 1/(sqrt2 sigma_y))
+// [ float4 s0[A*Tp] | float4 s1[A*Tp] | AgentParams prm[A] | float2 s2[A*Tp] ]
+//   s0[i] = (px_i, py_i, cos yaw_i, sin yaw_i)
+//   s1[i] = (yaw_i, v_i, px_{i-1}, py_{i-1})       previous position: CP pairs ego step i with agent
+//                                                    position i-1 (collision_probability.py:52)
+//   s2[i] = (1/(sqrt2 sigma_x), 1/(sqrt2 sigma_y)) of covariance i-1 (collision_probability.py:80)
 struct __align__(16) AgentParams {
   int32_t n_states;
   int32_t model;   // 0 = unprotected (LR1S ego / pedestrian logit), 1 = protected (LR4S both), 2 = none (harm 1)
@@ -35,17 +38,19 @@ struct __align__(16) AgentParams {
 struct AgentTableView {
   const float4* s0;
   const float4* s1;
+  const float2* s2;
   const AgentParams* prm;
 };
 
 __host__ __device__ inline size_t agent_table_bytes(int A, int Tp) {
-  return (size_t)A * Tp * 2 * sizeof(float4) + (size_t)A * sizeof(AgentParams);
+  return (size_t)A * Tp * (2 * sizeof(float4) + sizeof(float2)) + (size_t)A * sizeof(AgentParams);
 }
 __host__ __device__ inline AgentTableView agent_table_view(const void* base, int A, int Tp) {
   AgentTableView v;
   v.s0 = reinterpret_cast<const float4*>(base);
   v.s1 = v.s0 + (size_t)A * Tp;
   v.prm = reinterpret_cast<const AgentParams*>(v.s1 + (size_t)A * Tp);
+  v.s2 = reinterpret_cast<const float2*>(v.prm + A);
   return v;
 }
 

@@ -1,0 +1,432 @@
+// Dense metric core, sm_100a -- SUMMARY kernel (the throughput / latency path).
+//
+// Emits only what the planner consumes per trajectory: the validity mask (metrics/metric.py:50-98),
+// the summary vector and the flags.  Mapping (B200-first, not a translation of the reference loops):
+//
+//   * one warp owns one trajectory; its T ego states are staged once in shared memory;
+//   * the (agent, time) plane of an agent tile is FLATTENED over the lanes: lane l of chunk c works
+//     on flat index f = 32c + l -> (agent f / T, step f % T).  Every lane is busy for any T
+//     (31, 51, ...), consecutive lanes read consecutive agent-table entries (coalesced 16-byte
+//     loads through L1/L2; the table is at most a few hundred kB and shared by every warp);
+//   * the dense part per (n, a, i) is branch-light: oriented-box distance (SAT + 8 corner/box
+//     distances), harm logit, 5 m CP gate.  All per-trajectory quantities the reference derives
+//     from them are order-independent min/max reductions, so they are accumulated per lane and
+//     reduced once per trajectory (warp REDUX);
+//   * the expensive, sparse work is COMPACTED: evaluations inside the 5 m gate are pushed on a
+//     per-warp shared-memory queue and drained 32 at a time with all lanes active (36 erfc per
+//     item); colliding pairs are recorded with shared-memory atomics and handed to the
+//     warp-cooperative BE bisection afterwards;
+//   * max_t harm = logistic(max_t logit) (the logistic is monotone), so the dense loop needs no
+//     exp/div at all.
+//
+// Reference semantics per SURVEY.md appendix A; file:line citations are on the helpers in
+// fo_metric_dev.cuh and on the detail kernel (fo_metric_detail.cu), which computes the same numbers.
+#include "fo_metric_dev.cuh"
+
+namespace fo {
+
+constexpr int kFlatWarps = 8;
+constexpr int kTileAgents = 256;
+constexpr int kQueueCap = 64;
+
+__host__ __device__ inline size_t flat_warp_bytes(int T) {
+  size_t b = (size_t)kTileAgents * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kTileAgents * 4 + kQueueCap * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+struct WarpSmem {
+  unsigned long long* pairkey;  // [kTileAgents] (cp bits << 32 | (0xffff - t) << 16 | 1): argmax_t cp, first index on ties
+  float4* egoA;                 // [T] (x, y, cos theta, sin theta)
+  float2* egoB;                 // [T] (theta, v)
+  float* dist;                  // [T] cumulative chord length (BE)
+  uint32_t* colfirst;           // [kTileAgents] first step with rounded distance 0 (0xffffffff = none)
+  uint32_t* queue;              // [kQueueCap] gated (agent-in-tile << 8 | step) items
+};
+
+__device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int T) {
+  WarpSmem w;
+  w.pairkey = reinterpret_cast<unsigned long long*>(base);
+  w.egoA = reinterpret_cast<float4*>(w.pairkey + kTileAgents);
+  w.egoB = reinterpret_cast<float2*>(w.egoA + T);
+  w.dist = reinterpret_cast<float*>(w.egoB + T);
+  w.colfirst = reinterpret_cast<uint32_t*>(w.dist + T);
+  w.queue = w.colfirst + kTileAgents;
+  return w;
+}
+
+__device__ __forceinline__ AgentParams load_params(const AgentParams* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  int4 a = __ldg(q), b = __ldg(q + 1);
+  AgentParams r;
+  r.n_states = a.x; r.model = a.y; r.hl = __int_as_float(a.z); r.hw = __int_as_float(a.w);
+  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = 0.0f;
+  return r;
+}
+
+// harm logits (he = 1/(1+exp(-ze)), ho likewise); harm_model.py:81-105, logistic_regression.py:35-48,71-73
+__device__ __forceinline__ void harm_logits(const MetricKArgs& k, const AgentParams& P, float dv, float dxr, float dyr,
+                                            float th, float psi, float& ze, float& zo) {
+  if (P.model == 0) {
+    ze = fmaf(k.hc.ia_speed * P.ke, dv, k.hc.ia_const);
+    zo = fmaf(k.hc.ped_speed * P.ko, dv, -k.hc.ped_const);
+  } else if (P.model == 1) {
+    const float PI_F = 3.14159265358979323846f;
+    float rel = atan2f(dyr, dxr);
+    float ae = rel - th;
+    float ao = PI_F + rel - psi;
+    ze = fmaf(k.hc.rs_speed * P.ke, dv, k.hc.rs_const) + lr4s_coef(ae, k.hc.rs_side, k.hc.rs_rear);
+    zo = fmaf(k.hc.rs_speed * P.ko, dv, k.hc.rs_const) + lr4s_coef(ao, k.hc.rs_side, k.hc.rs_rear);
+  } else {
+    ze = CUDART_INF_F;
+    zo = CUDART_INF_F;
+  }
+}
+
+__device__ __forceinline__ float sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+// ---------------------------------------------------------------------------------------------
+// BE bisection for one pair, lanes = time steps (be.py:66-193); ego arrays come from shared memory.
+__device__ __noinline__ float be_bisect_flat(const MetricKArgs& k, const WarpSmem w, int a, int n_states, float hl,
+                                             float hw, float lo0, int lane, bool& range_err) {
+  const int T = k.T;
+  const int nA = min(T, n_states);
+  const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
+  const float dmax = w.dist[T - 1];
+  float lo = lo0, hi = 5.0f, cur = 0.0f;
+  for (int it = 0; it < 10; ++it) {
+    cur = 0.5f * (lo + hi);
+    bool hit = false, over = false;
+    float carry = 0.0f;
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      float vn = (i == 0) ? v0 : fmaxf(fmaf(-cur, (float)(i - 1) * k.dt, v1), 0.0f);   // be.py:109
+      float inc = (i < T) ? vn * k.dt : 0.0f;
+      float sc = inc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(kFull, sc, o);
+        if (lane >= o) sc += t;
+      }
+      const float q = carry + sc - inc;                                                 // be.py:113 dist_new[i]
+      carry += __shfl_sync(kFull, sc, 31);
+      if (i < T) {
+        if (q > dmax) over = true;            // interp1d bounds_error (be.py:117-124)
+        int lo_j = 0, hi_j = T - 1;           // numpy.interp: j = last index with dist[j] <= q
+        while (lo_j < hi_j) {
+          int mid = (lo_j + hi_j + 1) >> 1;
+          if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
+        }
+        const int j = lo_j;
+        const float dj = w.dist[j];
+        float4 A0 = w.egoA[j];
+        float xn = A0.x, yn = A0.y, tn = w.egoB[j].x;
+        if (j != T - 1 && dj != q) {
+          float4 A1 = w.egoA[j + 1];
+          float wq = q - dj;
+          float inv = 1.0f / (w.dist[j + 1] - dj);
+          xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
+          yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
+          tn = fmaf((w.egoB[j + 1].x - tn) * inv, wq, tn);
+        }
+        if (i < nA) {
+          float sn, cn;
+          sincosf(tn, &sn, &cn);
+          float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
+          float dx = (s0.x - xn) - k.wb * cn;
+          float dy = (s0.y - yn) - k.wb * sn;
+          float rx = fmaf(dx, cn, dy * sn), ry = fmaf(dy, cn, -dx * sn);
+          float c = fmaf(cn, s0.z, sn * s0.w), s = fmaf(s0.w, cn, -s0.z * sn);
+          hit |= obb_hit(rx, ry, c, s, k.hEx, k.hEy, hl, hw);
+        }
+      }
+    }
+    if (__any_sync(kFull, over)) { range_err = true; return CUDART_NAN_F; }
+    const bool any_hit = __any_sync(kFull, hit);
+    if (nA > 0 && !any_hit) hi = cur; else lo = cur;   // be.py:74-77
+    if (hi - lo < 0.1f) break;                         // be.py:79
+  }
+  return cur;
+}
+
+// cumulative chord length of the ego polyline (be.py:99) into w.dist
+__device__ __noinline__ void be_prepare(const WarpSmem w, int T, int lane) {
+  float carry = 0.0f;
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int i = i0 + lane;
+    float seg = 0.0f;
+    if (i >= 1 && i < T) {
+      float4 p = w.egoA[i], q = w.egoA[i - 1];
+      seg = sqrtf((p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y));
+    }
+    float sc = seg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(kFull, sc, o);
+      if (lane >= o) sc += t;
+    }
+    if (i < T) w.dist[i] = carry + sc;
+    carry += __shfl_sync(kFull, sc, 31);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(const __grid_constant__ MetricKArgs k) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int T = k.T;
+  const WarpSmem w = warp_smem(smem_raw + (size_t)wib * flat_warp_bytes(T), T);
+  const int warp0 = blockIdx.x * kFlatWarps + wib;
+  const int nwarps = gridDim.x * kFlatWarps;
+  const bool do_cp = k.mmask & FO_M_CP, do_dce = k.mmask & FO_M_DCE, do_hr = k.mmask & FO_M_HR,
+             do_be = k.mmask & FO_M_BE, do_ttc = k.mmask & FO_M_TTC;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int n = warp0; n < k.N; n += nwarps) {
+    // ---- stage the ego trajectory ------------------------------------------------------------
+    float amin = 0.0f;
+    const float* eg = k.ego + (size_t)n * T * 5;
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      float x = __ldg(eg + i * 5 + 0), y = __ldg(eg + i * 5 + 1), th = __ldg(eg + i * 5 + 2);
+      float v = __ldg(eg + i * 5 + 3);
+      amin = fminf(amin, __ldg(eg + i * 5 + 4));
+      float sn, cs;
+      sincosf(th, &sn, &cs);
+      w.egoA[i] = make_float4(x, y, cs, sn);
+      w.egoB[i] = make_float2(th, v);
+    }
+    __syncwarp();
+
+    // per-lane accumulators (order-independent reductions, finished once per trajectory)
+    uint32_t acc_rmin = 0xffffffu, acc_col = 0xffffffffu;
+    float acc_ze = -CUDART_INF_F, acc_zo = -CUDART_INF_F;
+    float acc_er = 0.0f, acc_or = 0.0f, acc_cp = 0.0f, acc_hwc = 0.0f;
+    float btn_all = 0.0f, rcd_all = 0.0f;   // warp-uniform
+    uint32_t flags = 0;
+    bool be_ready = false;
+    float be_lo0 = 0.0f;
+
+    for (int a0 = 0; a0 < k.A; a0 += kTileAgents) {
+      const int nAt = min(kTileAgents, k.A - a0);
+      for (int j = lane; j < nAt; j += 32) { w.pairkey[j] = 0ull; w.colfirst[j] = 0xffffffffu; }
+      __syncwarp();
+      const int F = nAt * T;
+      int al = 0, i = lane;
+      while (i >= T) { i -= T; ++al; }
+      int qn = 0;
+
+      for (int f0 = 0;; f0 += 32) {
+        const bool more = f0 < F;
+        if (more) {
+          // ================= dense part: one (agent, step) per lane ===========================
+          const bool active = f0 + lane < F;
+          bool ingate = false;
+          if (active) {
+            const int a = a0 + al;
+            const AgentParams P = load_params(k.tab.prm + a);
+            if (i < P.n_states) {
+              const size_t idx = (size_t)a * k.Tp + i;
+              const float4 s0 = __ldg(&k.tab.s0[idx]);
+              const float4 s1 = __ldg(&k.tab.s1[idx]);
+              const float4 EA = w.egoA[i];
+              const float2 EB = w.egoB[i];
+              const float c = fmaf(EA.z, s0.z, EA.w * s0.w);    // cos(yaw - theta)
+              const float s = fmaf(s0.w, EA.z, -s0.z * EA.w);   // sin(yaw - theta)
+              const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
+              if (do_dce) {                                     // i < min(T, n_states)
+                float dx = dxr - k.wb * EA.z, dy = dyr - k.wb * EA.w;
+                float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
+                float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw));
+                uint32_t r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);   // np.round(d, 3)
+                acc_rmin = min(acc_rmin, r);
+                if (r == 0u) atomicMin(&w.colfirst[al], (uint32_t)i);
+              }
+              if (do_hr && i < T - 1) {                          // t < min(T-1, n_states)
+                float dv2 = fmaxf(fmaf(EB.y, EB.y, s1.y * s1.y) - 2.0f * EB.y * s1.y * c, 0.0f);
+                float dv = sqrtf(dv2);
+                float ze, zo;
+                harm_logits(k, P, dv, dxr, dyr, EB.x, s1.x, ze, zo);
+                acc_ze = fmaxf(acc_ze, ze);
+                acc_zo = fmaxf(acc_zo, zo);
+              }
+              if (do_cp && i >= 1) {                             // 5 m gate, collision_probability.py:61-78
+                float mx = s1.z - EA.x, my = s1.w - EA.y;
+                float hx = P.hlb * s0.z, hy = P.hlb * s0.w;
+                float d0 = fmaf(mx, mx, my * my);
+                float d1 = fmaf(mx + hx, mx + hx, (my + hy) * (my + hy));
+                float d2 = fmaf(mx - hx, mx - hx, (my - hy) * (my - hy));
+                ingate = fminf(d0, fminf(d1, d2)) <= 25.0f;
+              }
+            }
+          }
+          const unsigned b = __ballot_sync(kFull, ingate);
+          if (b) {
+            if (ingate) w.queue[qn + __popc(b & lt_mask)] = ((uint32_t)al << 8) | (uint32_t)i;
+            qn += __popc(b);
+            __syncwarp();
+          }
+          i += 32;
+          while (i >= T) { i -= T; ++al; }
+        }
+        // ================= sparse part: drain gated evaluations, 32 per round =====================
+        while (qn >= 32 || (!more && qn > 0)) {
+          const int cnt = min(qn, 32);
+          uint32_t item = 0;
+          if (lane < cnt) item = w.queue[qn - cnt + lane];
+          qn -= cnt;
+          __syncwarp();
+          if (lane < cnt) {
+            const int ial = (int)(item >> 8), ii = (int)(item & 0xffu), t = ii - 1;
+            const int a = a0 + ial;
+            const AgentParams P = load_params(k.tab.prm + a);
+            const size_t idx = (size_t)a * k.Tp + ii;
+            const float4 s0i = __ldg(&k.tab.s0[idx]);
+            const float4 s1i = __ldg(&k.tab.s1[idx]);
+            const float2 s2i = __ldg(&k.tab.s2[idx]);
+            const float4 Ei = w.egoA[ii];
+            // CP: 3 obstacle points x 3 axis-aligned ego boxes (collision_probability.py:94-122)
+            const float mx = s1i.z - Ei.x, my = s1i.w - Ei.y;
+            const float hx = P.hlb * s0i.z, hy = P.hlb * s0i.w;
+            const float bx = k.L3 * Ei.z, by = k.L3 * Ei.w;
+            float prob = 0.0f;
+#pragma unroll 1
+            for (int mb = 0; mb < 9; ++mb) {
+              const int m = mb / 3, bb = mb - 3 * m;
+              const float fm = (m == 0) ? 0.0f : (m == 1 ? 1.0f : -1.0f);
+              const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
+              const float ux = fmaf(fm, hx, mx), uy = fmaf(fm, hy, my);
+              const float cxb = fb * bx, cyb = fb * by;
+              float px = half_derf((cxb - k.L6 - ux) * s2i.x, (cxb + k.L6 - ux) * s2i.x);
+              float py = half_derf((cyb - k.W2 - uy) * s2i.y, (cyb + k.W2 - uy) * s2i.y);
+              prob = fmaf(px, py, prob);
+            }
+            const float cp = prob * (1.0f / 3.0f);
+            acc_cp = fmaxf(acc_cp, cp);
+            if (do_hr) {                       // risk[t] = harm[t] * cp[t], cp[t] = CP of step t+1 (hr.py:78-79)
+              const float4 s0t = __ldg(&k.tab.s0[idx - 1]);
+              const float4 s1t = __ldg(&k.tab.s1[idx - 1]);
+              const float4 Et = w.egoA[t];
+              const float2 EtB = w.egoB[t];
+              const float ct = fmaf(Et.z, s0t.z, Et.w * s0t.w);
+              const float dv = sqrtf(fmaxf(fmaf(EtB.y, EtB.y, s1t.y * s1t.y) - 2.0f * EtB.y * s1t.y * ct, 0.0f));
+              float ze, zo;
+              harm_logits(k, P, dv, s0t.x - Et.x, s0t.y - Et.y, EtB.x, s1t.x, ze, zo);
+              acc_er = fmaxf(acc_er, sigmoid(ze) * cp);
+              acc_or = fmaxf(acc_or, sigmoid(zo) * cp);
+              if (cp > 0.01f)                  // candidates for obst_harm[argmax cp] (hr.py:81-84)
+                atomicMax(&w.pairkey[ial], ((unsigned long long)__float_as_uint(cp) << 32) |
+                                               ((unsigned long long)(0xffffu - (unsigned)t) << 16) | 1ull);
+            }
+          }
+          __syncwarp();
+        }
+        if (!more) break;
+      }
+
+      // ================= tile epilogue: harm_with_cp, wttc, BE ======================================
+      for (int j0 = 0; j0 < nAt; j0 += 32) {
+        const int j = j0 + lane;
+        const unsigned long long key = (j < nAt) ? w.pairkey[j] : 0ull;
+        const uint32_t cf = (j < nAt) ? w.colfirst[j] : 0xffffffffu;
+        if (key != 0ull) {
+          const int t = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
+          const int a = a0 + j;
+          const AgentParams P = load_params(k.tab.prm + a);
+          const size_t idx = (size_t)a * k.Tp + t;
+          const float4 s0t = __ldg(&k.tab.s0[idx]);
+          const float4 s1t = __ldg(&k.tab.s1[idx]);
+          const float4 Et = w.egoA[t];
+          const float2 EtB = w.egoB[t];
+          const float ct = fmaf(Et.z, s0t.z, Et.w * s0t.w);
+          const float dv = sqrtf(fmaxf(fmaf(EtB.y, EtB.y, s1t.y * s1t.y) - 2.0f * EtB.y * s1t.y * ct, 0.0f));
+          float ze, zo;
+          harm_logits(k, P, dv, s0t.x - Et.x, s0t.y - Et.y, EtB.x, s1t.x, ze, zo);
+          acc_hwc = fmaxf(acc_hwc, sigmoid(zo));
+        }
+        if (do_ttc) acc_col = min(acc_col, cf);
+        if (do_be && do_ttc) {
+          unsigned m = __ballot_sync(kFull, cf != 0xffffffffu && cf > 0u);   // be.py:49-50
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int a = a0 + j0 + src;
+            const AgentParams P = load_params(k.tab.prm + a);
+            if (!be_ready) {
+              be_prepare(w, T, lane);
+              float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));
+              be_lo0 = rintf(am * 100.0f) / 100.0f;                          // be.py:68
+              be_ready = true;
+            }
+            bool range_err = false;
+            const float rcd = be_bisect_flat(k, w, a, P.n_states, P.hl, P.hw, be_lo0, lane, range_err);
+            if (range_err) flags |= FO_F_BE_RANGE;
+            rcd_all = fmaxf(rcd_all, rcd);
+            btn_all = fmaxf(btn_all, rcd / k.a_max);
+          }
+        }
+      }
+      __syncwarp();
+    }  // agent tiles
+
+    // ---- per-trajectory reduction and threshold mask (metric.py:50-98) ----------------------------
+    const float er = umaxf(acc_er), orr = umaxf(acc_or), cpm = umaxf(acc_cp), hwc_all = umaxf(acc_hwc);
+    float ze = acc_ze, zo = acc_zo;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ze = fmaxf(ze, __shfl_xor_sync(kFull, ze, o));
+      zo = fmaxf(zo, __shfl_xor_sync(kFull, zo, o));
+    }
+    const uint32_t rmin = __reduce_min_sync(kFull, acc_rmin);
+    const uint32_t col = __reduce_min_sync(kFull, acc_col);
+    if (lane == 0) {
+      const float eh = sigmoid(ze), oh = sigmoid(zo);   // logistic is monotone: max harm = logistic(max logit)
+      const bool has_agents = k.A > 0 && k.mmask != 0;
+      const double dce_min = (double)rmin / 1000.0;
+      const bool has_col = col != 0xffffffffu;
+      const double wttc = has_col ? rint((double)col * k.dtd * 1000.0) / 1000.0 : (double)CUDART_INF;
+      bool ok = true;
+      if (has_agents) {
+        if (do_be && (k.tmask & FO_T_BE) && (double)btn_all > k.thr_be) ok = false;
+        if (do_hr && (k.tmask & FO_T_HARM) && (double)hwc_all > k.thr_harm) ok = false;
+        if (do_hr && (k.tmask & FO_T_RISK) && (double)orr > k.thr_risk) ok = false;
+        if (do_hr && (k.tmask & FO_T_CP) && (double)cpm > k.thr_cp) ok = false;
+        if (do_ttc && (k.tmask & FO_T_TTC) && has_col && wttc < k.thr_ttc) ok = false;
+        if (do_dce && (k.tmask & FO_T_DCE) && rmin != 0xffffffu && dce_min < k.thr_dce) ok = false;
+        if (flags & FO_F_BE_RANGE) ok = false;
+      }
+      k.valid[n] = ok ? 1 : 0;
+      if (k.flags) k.flags[n] = flags;
+      if (k.summary) {
+        float* sm = k.summary + (size_t)n * FO_SUMMARY_K;
+        sm[0] = er; sm[1] = orr; sm[2] = do_hr ? eh : 0.0f; sm[3] = do_hr ? oh : 0.0f; sm[4] = cpm; sm[5] = hwc_all;
+        sm[6] = (rmin == 0xffffffu || !do_dce) ? CUDART_INF_F : (float)dce_min;
+        sm[7] = has_col ? (float)wttc : CUDART_INF_F;
+        sm[8] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : btn_all;
+        sm[9] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd_all;
+      }
+    }
+  }
+}
+
+int launch_metric_flat(const MetricKArgs& k, int num_sms, cudaStream_t st) {
+  const size_t smem = flat_warp_bytes(k.T) * kFlatWarps;
+  static size_t configured = 0;
+  if (smem > configured) {
+    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int per_sm = 1;
+  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_flat_kernel, kFlatWarps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int ctas_needed = (k.N + kFlatWarps - 1) / kFlatWarps;
+  const int full = num_sms * per_sm;
+  const int grid = ctas_needed < full ? ctas_needed : full;   // persistent: warps stride over trajectories
+  fo_metric_flat_kernel<<<grid, kFlatWarps * 32, smem, st>>>(k);
+  count_launch();
+  FO_CUDA_TRY(cudaGetLastError());
+  return FO_OK;
+}
+
+}  // namespace fo

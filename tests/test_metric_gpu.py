@@ -87,21 +87,52 @@ def test_latency_config_parity(cuda_device):
     _check(rep)
 
 
-def test_summary_only_equals_detail_path(cuda_device):
-    """Summary-only launch (the bench path) must give the same valid/summary as the detail launch."""
-    case = S.make_case(3000, 48, 51, seed=9)
+def test_summary_kernel_equals_detail_kernel(cuda_device):
+    """The flat summary kernel (bench / planner path) against the detail kernel at a size the CPU
+    oracle would need minutes for: identical masks/flags/discrete values, floats to 1e-5."""
+    case = S.make_case(3000, 300, 51, seed=9)       # > 256 agents: exercises agent tiling
     res_d, _ = parity.run_gpu(case, want_pair=True, want_step=True)
     res_s, _ = parity.run_gpu(case, want_pair=False, want_step=False)
     assert np.array_equal(res_d["valid"], res_s["valid"])
     assert np.array_equal(res_d["flags"], res_s["flags"])
-    assert np.array_equal(res_d["summary"], res_s["summary"], equal_nan=True)
+    ok = (res_d["flags"] & 1) == 0
+    for col in (6, 7):                                # min dce, wttc: discrete
+        assert np.array_equal(res_d["summary"][:, col], res_s["summary"][:, col])
+    for col in (8, 9):
+        assert np.array_equal(res_d["summary"][ok, col], res_s["summary"][ok, col])
+    for col in range(6):
+        np.testing.assert_allclose(res_s["summary"][:, col], res_d["summary"][:, col], rtol=1e-5, atol=1e-7)
     # and the summary is the reduction of the per-pair detail
     p = res_d["pair"]
-    ok = (res_d["flags"] & 1) == 0
     assert np.array_equal(res_d["summary"][:, 6], p[..., 0].min(1))
     assert np.array_equal(res_d["summary"][ok, 8], p[ok][..., 10].max(1))
     for col_s, col_p in ((0, 2), (1, 3), (2, 6), (3, 7), (4, 8), (5, 5)):
         assert np.array_equal(res_d["summary"][:, col_s], p[..., col_p].max(1))
+
+
+@pytest.mark.parametrize("seed,n,a,t", [(31, 500, 32, 31), (32, 200, 40, 51), (33, 100, 7, 2), (34, 64, 300, 31)])
+def test_summary_kernel_matches_oracle(seed, n, a, t, cuda_device):
+    case = S.make_case(n, a, t, seed=seed)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    _check(parity.compare_bundle(out, res, case))
+
+
+@pytest.mark.parametrize("metrics,thr", [
+    (["hr", "ttc", "ttce", "dce", "wttc", "cp"], {"harm": 0.1, "risk": 1, "be": None, "cp": None, "ttc": None, "dce": None}),
+    (["dce", "ttc"], {"harm": None, "risk": None, "be": None, "cp": None, "ttc": 1.2, "dce": 0.75}),
+    (["cp"], {"harm": 0.1, "risk": 1, "be": None, "cp": 0.1, "ttc": None, "dce": None}),
+    (["hr"], {"harm": 0.2, "risk": 0.02, "be": None, "cp": 0.15, "ttc": None, "dce": None}),
+    (["be", "ttc"], {"harm": None, "risk": None, "be": 0.25, "cp": None, "ttc": None, "dce": None}),
+])
+def test_metric_subsets_and_thresholds(metrics, thr, cuda_device):
+    """Activation subsets / armed thresholds (metric.py:50-98, 125-147) on both kernels."""
+    case = S.make_case(300, 24, 31, seed=41, activated_metrics=metrics, thresholds={**thr, "wttc": None, "ttce": None})
+    out = MO.evaluate_bundle(case)
+    for detail in (True, False):
+        res, eng = parity.run_gpu(case, want_pair=detail, want_step=detail)
+        assert eng.order == out["order"]
+        _check(parity.compare_bundle(out, res, case))
 
 
 def test_edge_cases(cuda_device):
