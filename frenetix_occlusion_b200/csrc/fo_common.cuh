@@ -32,7 +32,7 @@ struct __align__(16) AgentParams {
   float hl, hw;    // half extents of the unbuffered agent.shape  (DCE, BE)
   float hlb;       // half of the buffered prediction length     (CP front/back points)
   float ke, ko;    // m_o/(m_e+m_o), m_e/(m_e+m_o)               (harm_model.py:96-97)
-  float pad;
+  float pad;       // circumradius sqrt(hl^2 + hw^2)
 };
 
 struct AgentTableView {

@@ -57,7 +57,7 @@ __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, 
     float mo = obstacle_mass(raw.kind[idx], raw.buf_length[idx] * raw.buf_width[idx]);  // harm_model.py:73,78
     p.ke = mo / (m_ego + mo);
     p.ko = m_ego / (m_ego + mo);
-    p.pad = 0.0f;
+    p.pad = sqrtf(p.hl * p.hl + p.hw * p.hw);   // circumradius of the unbuffered rectangle (distance lower bound)
     prm[idx] = p;
   }
 }

@@ -21,6 +21,8 @@
 //
 // Reference semantics per SURVEY.md appendix A; file:line citations are on the helpers in
 // fo_metric_dev.cuh and on the detail kernel (fo_metric_detail.cu), which computes the same numbers.
+#include <stdlib.h>
+
 #include "fo_metric_dev.cuh"
 
 namespace fo {
@@ -28,9 +30,10 @@ namespace fo {
 constexpr int kFlatWarps = 8;
 constexpr int kTileAgents = 256;
 constexpr int kQueueCap = 64;
+constexpr int kInvBuckets = 64;   // arc-length -> state-index lookup used by the BE interpolation
 
 __host__ __device__ inline size_t flat_warp_bytes(int T) {
-  size_t b = (size_t)kTileAgents * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kTileAgents * 4 + kQueueCap * 4;
+  size_t b = (size_t)kTileAgents * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kTileAgents * 4 + kQueueCap * 4 + kInvBuckets + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -41,6 +44,7 @@ struct WarpSmem {
   float* dist;                  // [T] cumulative chord length (BE)
   uint32_t* colfirst;           // [kTileAgents] first step with rounded distance 0 (0xffffffff = none)
   uint32_t* queue;              // [kQueueCap] gated (agent-in-tile << 8 | step) items
+  uint8_t* inv;                 // [kInvBuckets + 1] last state index with dist <= b * dmax / kInvBuckets
 };
 
 __device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int T) {
@@ -51,6 +55,7 @@ __device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int T) {
   w.dist = reinterpret_cast<float*>(w.egoB + T);
   w.colfirst = reinterpret_cast<uint32_t*>(w.dist + T);
   w.queue = w.colfirst + kTileAgents;
+  w.inv = reinterpret_cast<uint8_t*>(w.queue + kQueueCap);
   return w;
 }
 
@@ -59,7 +64,7 @@ __device__ __forceinline__ AgentParams load_params(const AgentParams* p) {
   int4 a = __ldg(q), b = __ldg(q + 1);
   AgentParams r;
   r.n_states = a.x; r.model = a.y; r.hl = __int_as_float(a.z); r.hw = __int_as_float(a.w);
-  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = 0.0f;
+  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = __int_as_float(b.w);
   return r;
 }
 
@@ -82,6 +87,29 @@ __device__ __forceinline__ void harm_logits(const MetricKArgs& k, const AgentPar
   }
 }
 
+// Dense-loop variant: only the running maxima of the logits are needed, so the LR4S impact-angle
+// class (atan2 + comparisons) is evaluated only when the upper bound logit (largest area
+// coefficient) could still raise one of the maxima.  Exact: skipped evaluations cannot change a max.
+__device__ __forceinline__ void harm_logits_max(const MetricKArgs& k, const AgentParams& P, float dv, float dxr,
+                                                float dyr, float th, float psi, float& acc_ze, float& acc_zo) {
+  if (P.model == 0) {
+    acc_ze = fmaxf(acc_ze, fmaf(k.hc.ia_speed * P.ke, dv, k.hc.ia_const));
+    acc_zo = fmaxf(acc_zo, fmaf(k.hc.ped_speed * P.ko, dv, -k.hc.ped_const));
+  } else if (P.model == 1) {
+    const float cmax = fmaxf(0.0f, fmaxf(k.hc.rs_side, k.hc.rs_rear));
+    const float be = fmaf(k.hc.rs_speed * P.ke, dv, k.hc.rs_const), bo = fmaf(k.hc.rs_speed * P.ko, dv, k.hc.rs_const);
+    if (be + cmax > acc_ze || bo + cmax > acc_zo) {
+      const float PI_F = 3.14159265358979323846f;
+      float rel = atan2f(dyr, dxr);
+      acc_ze = fmaxf(acc_ze, be + lr4s_coef(rel - th, k.hc.rs_side, k.hc.rs_rear));
+      acc_zo = fmaxf(acc_zo, bo + lr4s_coef(PI_F + rel - psi, k.hc.rs_side, k.hc.rs_rear));
+    }
+  } else {
+    acc_ze = CUDART_INF_F;
+    acc_zo = CUDART_INF_F;
+  }
+}
+
 __device__ __forceinline__ float sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,30 +120,31 @@ __device__ __noinline__ float be_bisect_flat(const MetricKArgs& k, const WarpSme
   const int nA = min(T, n_states);
   const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
   const float dmax = w.dist[T - 1];
+  const float inv_w = dmax > 0.0f ? (float)kInvBuckets / dmax : 0.0f;
   float lo = lo0, hi = 5.0f, cur = 0.0f;
   for (int it = 0; it < 10; ++it) {
     cur = 0.5f * (lo + hi);
     bool hit = false, over = false;
-    float carry = 0.0f;
+    // v_new[0] = v0, v_new[k+1] = max(v1 - cur*k*dt, 0) (be.py:109); dist_new[i] = dt * sum_{k<i} v_new[k]
+    // (be.py:113) in closed form: the clipped arithmetic series has mpos = floor(v1/(cur*dt)) + 1 positive terms.
+    const float step = cur * k.dt;
+    const float mpos = (step > 0.0f) ? fmaxf(floorf(__fdividef(v1, step)) + 1.0f, 0.0f) : 1.0e9f;
     for (int i0 = 0; i0 < T; i0 += 32) {
       const int i = i0 + lane;
-      float vn = (i == 0) ? v0 : fmaxf(fmaf(-cur, (float)(i - 1) * k.dt, v1), 0.0f);   // be.py:109
-      float inc = (i < T) ? vn * k.dt : 0.0f;
-      float sc = inc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float t = __shfl_up_sync(kFull, sc, o);
-        if (lane >= o) sc += t;
-      }
-      const float q = carry + sc - inc;                                                 // be.py:113 dist_new[i]
-      carry += __shfl_sync(kFull, sc, 31);
       if (i < T) {
+        const float m = fminf((float)(i - 1), mpos);                  // terms of the series included (i >= 1)
+        const float q = (i == 0) ? 0.0f : k.dt * (v0 + fmaf(m, v1, -0.5f * step * m * (m - 1.0f)));
         if (q > dmax) over = true;            // interp1d bounds_error (be.py:117-124)
-        int lo_j = 0, hi_j = T - 1;           // numpy.interp: j = last index with dist[j] <= q
+        // numpy.interp: j = last index with dist[j] <= q.  Bracket from the arc-length lookup table,
+        // bisect inside the bracket, then guard against a float32 off-by-one in the bucket index.
+        const int b = min(__float2int_rd(q * inv_w), kInvBuckets - 1);
+        int lo_j = w.inv[b], hi_j = w.inv[b + 1];
         while (lo_j < hi_j) {
-          int mid = (lo_j + hi_j + 1) >> 1;
+          const int mid = (lo_j + hi_j + 1) >> 1;
           if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
         }
+        while (lo_j > 0 && w.dist[lo_j] > q) --lo_j;
+        while (lo_j < T - 1 && w.dist[lo_j + 1] <= q) ++lo_j;
         const int j = lo_j;
         const float dj = w.dist[j];
         float4 A0 = w.egoA[j];
@@ -130,7 +159,7 @@ __device__ __noinline__ float be_bisect_flat(const MetricKArgs& k, const WarpSme
         }
         if (i < nA) {
           float sn, cn;
-          sincosf(tn, &sn, &cn);
+          __sincosf(tn, &sn, &cn);
           float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
           float dx = (s0.x - xn) - k.wb * cn;
           float dy = (s0.y - yn) - k.wb * sn;
@@ -168,10 +197,24 @@ __device__ __noinline__ void be_prepare(const WarpSmem w, int T, int lane) {
     carry += __shfl_sync(kFull, sc, 31);
   }
   __syncwarp();
+  const float bw = w.dist[T - 1] / (float)kInvBuckets;
+  for (int b = lane; b <= kInvBuckets; b += 32) {
+    const float q = (b == kInvBuckets) ? CUDART_INF_F : (float)b * bw;
+    int lo_j = 0, hi_j = T - 1;
+    while (lo_j < hi_j) {
+      const int mid = (lo_j + hi_j + 1) >> 1;
+      if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
+    }
+    w.inv[b] = (uint8_t)lo_j;
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(const __grid_constant__ MetricKArgs k) {
+// MASK: compile-time metric mask (0 = read k.mmask at run time).  PRUNE: skip the exact oriented-box
+// distance when a circumcircle lower bound proves it cannot lower the lane's running minimum.
+template <uint32_t MASK, bool PRUNE, int MINB>
+__global__ void __launch_bounds__(kFlatWarps * 32, MINB) fo_metric_flat_kernel(const __grid_constant__ MetricKArgs k) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -179,9 +222,11 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
   const WarpSmem w = warp_smem(smem_raw + (size_t)wib * flat_warp_bytes(T), T);
   const int warp0 = blockIdx.x * kFlatWarps + wib;
   const int nwarps = gridDim.x * kFlatWarps;
-  const bool do_cp = k.mmask & FO_M_CP, do_dce = k.mmask & FO_M_DCE, do_hr = k.mmask & FO_M_HR,
-             do_be = k.mmask & FO_M_BE, do_ttc = k.mmask & FO_M_TTC;
+  const uint32_t mm = MASK ? MASK : k.mmask;
+  const bool do_cp = mm & FO_M_CP, do_dce = mm & FO_M_DCE, do_hr = mm & FO_M_HR, do_be = mm & FO_M_BE,
+             do_ttc = mm & FO_M_TTC;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const float rE = sqrtf(k.hEx * k.hEx + k.hEy * k.hEy);   // ego circumradius
 
   for (int n = warp0; n < k.N; n += nwarps) {
     // ---- stage the ego trajectory ------------------------------------------------------------
@@ -236,20 +281,25 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
               const float s = fmaf(s0.w, EA.z, -s0.z * EA.w);   // sin(yaw - theta)
               const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
               if (do_dce) {                                     // i < min(T, n_states)
-                float dx = dxr - k.wb * EA.z, dy = dyr - k.wb * EA.w;
-                float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
-                float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw));
-                uint32_t r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);   // np.round(d, 3)
-                acc_rmin = min(acc_rmin, r);
-                if (r == 0u) atomicMin(&w.colfirst[al], (uint32_t)i);
+                const float dx = dxr - k.wb * EA.z, dy = dyr - k.wb * EA.w;   // centre to centre
+                bool need = true;
+                if (PRUNE) {
+                  // distance >= |centres| - rE - rO; skip when that bound is >= running min + 2 mm
+                  const float lim = rE + P.pad + (float)(acc_rmin + 2u) * 0.001f;
+                  need = fmaf(dx, dx, dy * dy) < lim * lim;
+                }
+                if (need) {
+                  float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
+                  float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw));
+                  uint32_t r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);   // np.round(d, 3)
+                  acc_rmin = min(acc_rmin, r);
+                  if (r == 0u) atomicMin(&w.colfirst[al], (uint32_t)i);
+                }
               }
               if (do_hr && i < T - 1) {                          // t < min(T-1, n_states)
                 float dv2 = fmaxf(fmaf(EB.y, EB.y, s1.y * s1.y) - 2.0f * EB.y * s1.y * c, 0.0f);
-                float dv = sqrtf(dv2);
-                float ze, zo;
-                harm_logits(k, P, dv, dxr, dyr, EB.x, s1.x, ze, zo);
-                acc_ze = fmaxf(acc_ze, ze);
-                acc_zo = fmaxf(acc_zo, zo);
+                float dv = dv2 * rsqrtf(fmaxf(dv2, 1e-30f));        // |dv|, ~2 ulp: harm tolerance is 1e-4
+                harm_logits_max(k, P, dv, dxr, dyr, EB.x, s1.x, acc_ze, acc_zo);
               }
               if (do_cp && i >= 1) {                             // 5 m gate, collision_probability.py:61-78
                 float mx = s1.z - EA.x, my = s1.w - EA.y;
@@ -268,7 +318,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
             __syncwarp();
           }
           i += 32;
-          while (i >= T) { i -= T; ++al; }
+          if (T >= 32) { if (i >= T) { i -= T; ++al; } }
+          else { while (i >= T) { i -= T; ++al; } }
         }
         // ================= sparse part: drain gated evaluations, 32 per round =====================
         while (qn >= 32 || (!more && qn > 0)) {
@@ -298,9 +349,13 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
               const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
               const float ux = fmaf(fm, hx, mx), uy = fmaf(fm, hy, my);
               const float cxb = fb * bx, cyb = fb * by;
-              float px = half_derf((cxb - k.L6 - ux) * s2i.x, (cxb + k.L6 - ux) * s2i.x);
+              // the narrow (width) factor first; a term whose factor is below 1e-10 contributes less than
+              // 1e-10 to a probability compared at an absolute floor of 2e-7 and is dropped
               float py = half_derf((cyb - k.W2 - uy) * s2i.y, (cyb + k.W2 - uy) * s2i.y);
-              prob = fmaf(px, py, prob);
+              if (py > 1e-10f) {
+                float px = half_derf((cxb - k.L6 - ux) * s2i.x, (cxb + k.L6 - ux) * s2i.x);
+                prob = fmaf(px, py, prob);
+              }
             }
             const float cp = prob * (1.0f / 3.0f);
             acc_cp = fmaxf(acc_cp, cp);
@@ -382,7 +437,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
     const uint32_t col = __reduce_min_sync(kFull, acc_col);
     if (lane == 0) {
       const float eh = sigmoid(ze), oh = sigmoid(zo);   // logistic is monotone: max harm = logistic(max logit)
-      const bool has_agents = k.A > 0 && k.mmask != 0;
+      const bool has_agents = k.A > 0 && mm != 0;
       const double dce_min = (double)rmin / 1000.0;
       const bool has_col = col != 0xffffffffu;
       const double wttc = has_col ? rint((double)col * k.dtd * 1000.0) / 1000.0 : (double)CUDART_INF;
@@ -410,23 +465,37 @@ __global__ void __launch_bounds__(kFlatWarps * 32, 3) fo_metric_flat_kernel(cons
   }
 }
 
-int launch_metric_flat(const MetricKArgs& k, int num_sms, cudaStream_t st) {
+template <uint32_t MASK, bool PRUNE, int MINB>
+static int launch_flat_inst(const MetricKArgs& k, int num_sms, cudaStream_t st) {
   const size_t smem = flat_warp_bytes(k.T) * kFlatWarps;
   static size_t configured = 0;
-  if (smem > configured) {
-    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int per_sm = 1;
+  if (smem != configured) {
+    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_flat_kernel<MASK, PRUNE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_flat_kernel<MASK, PRUNE, MINB>,
+                                                              kFlatWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
     configured = smem;
   }
-  int per_sm = 1;
-  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_flat_kernel, kFlatWarps * 32, smem));
-  if (per_sm < 1) per_sm = 1;
   const int ctas_needed = (k.N + kFlatWarps - 1) / kFlatWarps;
   const int full = num_sms * per_sm;
   const int grid = ctas_needed < full ? ctas_needed : full;   // persistent: warps stride over trajectories
-  fo_metric_flat_kernel<<<grid, kFlatWarps * 32, smem, st>>>(k);
+  fo_metric_flat_kernel<MASK, PRUNE, MINB><<<grid, kFlatWarps * 32, smem, st>>>(k);
   count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;
+}
+
+int launch_metric_flat(const MetricKArgs& k, int num_sms, cudaStream_t st) {
+  constexpr uint32_t kAll = FO_M_CP | FO_M_DCE | FO_M_TTC | FO_M_HR | FO_M_BE | FO_M_TTCE | FO_M_WTTC;
+  constexpr uint32_t kDefault = kAll & ~FO_M_BE;   // occlusion.yaml:12-18
+  static const bool no_prune = getenv("FO_NO_PRUNE") != nullptr;   // measurement switch
+  static const bool minb4 = getenv("FO_FLAT_MINB4") != nullptr;     // occupancy experiment switch (64 regs, spills)
+  if (no_prune) return launch_flat_inst<0u, false, 3>(k, num_sms, st);
+  if (k.mmask == kAll) return minb4 ? launch_flat_inst<kAll, true, 4>(k, num_sms, st) : launch_flat_inst<kAll, true, 3>(k, num_sms, st);
+  if (k.mmask == kDefault) return launch_flat_inst<kDefault, true, 3>(k, num_sms, st);
+  return launch_flat_inst<0u, true, 3>(k, num_sms, st);
 }
 
 }  // namespace fo
