@@ -164,6 +164,7 @@ def run_ours(args):
     import torch.distributed as dist
     from frenetix_occlusion_b200 import _lib as L
     from frenetix_occlusion_b200.engine import AgentSet, MetricEngine, BundleResult
+    from frenetix_occlusion_b200.parallel import ResultGatherer, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,8 +179,7 @@ def run_ours(args):
     wl = workload(args.workload)
     N_total, A, T = wl["n_traj"], wl["n_agents"], wl["n_states"]
     # contiguous trajectory shard of this rank (strong scaling)
-    per = (N_total + world - 1) // world
-    lo, hi = rank * per, min(N_total, (rank + 1) * per)
+    lo, hi = shard_bounds(N_total, world, rank)
     n_local = hi - lo
     assert lo % CHUNK == 0 or world == 1 or N_total < CHUNK, "shards must align with generation chunks"
     case = make_case(wl, n_local, first_chunk=lo // CHUNK)
@@ -191,25 +191,20 @@ def run_ours(args):
     out = BundleResult(torch.empty(n_local, dtype=torch.uint8, device=dev),
                        torch.empty((n_local, L.FO_SUMMARY_K), dtype=torch.float32, device=dev),
                        torch.empty(n_local, dtype=torch.int32, device=dev))
-    if world > 1:
-        g_valid = torch.empty(per * world, dtype=torch.uint8, device=dev)
-        g_summary = torch.empty((per * world, L.FO_SUMMARY_K), dtype=torch.float32, device=dev)
-        pad_valid = torch.zeros(per, dtype=torch.uint8, device=dev)
-        pad_summary = torch.zeros((per, L.FO_SUMMARY_K), dtype=torch.float32, device=dev)
+    gatherer = ResultGatherer(N_total, L.FO_SUMMARY_K, dev) if world > 1 else None
     host_valid = torch.empty(n_local, dtype=torch.uint8).pin_memory()
     host_summary = torch.empty((n_local, L.FO_SUMMARY_K), dtype=torch.float32).pin_memory()
 
     def step_resident():
         eng.assess(ego_dev, out=out)
         if world > 1:   # the single collective of the path: all-gather of the result vectors
-            pad_valid[:n_local].copy_(out.valid)
-            pad_summary[:n_local].copy_(out.summary)
-            dist.all_gather_into_tensor(g_valid, pad_valid)
-            dist.all_gather_into_tensor(g_summary, pad_summary)
+            gatherer.gather(out.valid, out.summary, out.flags)
 
     def step_e2e():
         d = ego_host.to(dev, non_blocking=True)          # H2D of this step's inputs from pinned memory
         eng.assess(d, out=out)
+        if world > 1:
+            gatherer.gather(out.valid, out.summary, out.flags)
         host_valid.copy_(out.valid, non_blocking=True)   # D2H of the step's result
         host_summary.copy_(out.summary, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -238,10 +233,7 @@ def run_ours(args):
                 b.record()
                 kern.append((a, b))
                 if world > 1:
-                    pad_valid[:n_local].copy_(out.valid)
-                    pad_summary[:n_local].copy_(out.summary)
-                    dist.all_gather_into_tensor(g_valid, pad_valid)
-                    dist.all_gather_into_tensor(g_summary, pad_summary)
+                    gatherer.gather(out.valid, out.summary, out.flags)
             else:
                 fn()
         e1.record()
@@ -295,7 +287,7 @@ def run_ours(args):
     evals_local = n_local * A * (T - 1)
     achieved_tflops = evals_local * flop_per_eval / (k_ms * 1e-3) / 1e12
     alg_bytes = n_local * (T * 5 * 4 + 1 + 4 + 4 * L.FO_SUMMARY_K) + A * T * 32
-    roofline = {"bound": "fp32", "kernel": "fo_metric_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
+    roofline = {"bound": "fp32", "kernel": "fo_metric_flat_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
                 "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "peak_source": peak_src,
                 "kernel_ms": k_ms, "flop_per_eval": flop_per_eval, "gate_fraction": g_frac, "be_pair_fraction": be_pairs,
                 "traffic": None,

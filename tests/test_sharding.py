@@ -1,0 +1,63 @@
+"""World-size-2 gloo test (CPU) of the N>1 host logic: contiguous trajectory shards + the single
+all-gather of the result vectors reassemble the global result exactly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fake_results(lo, hi, k):
+    idx = torch.arange(lo, hi, dtype=torch.float32)
+    valid = (torch.arange(lo, hi) % 3 == 0).to(torch.uint8)
+    summary = idx[:, None] * 0.5 + torch.arange(k, dtype=torch.float32)[None]
+    flags = (torch.arange(lo, hi) % 7 == 0).to(torch.int32)
+    return valid, summary, flags
+
+
+def _worker(rank, world, n_total, port, q):
+    sys.path.insert(0, ROOT)
+    from frenetix_occlusion_b200.parallel import ResultGatherer, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_bounds(n_total, world, rank)
+        g = ResultGatherer(n_total, 10, torch.device("cpu"))
+        v, s, f = _fake_results(lo, hi, 10)
+        gv, gs, gf = g.gather(v, s, f)
+        ev, es, ef = _fake_results(0, n_total, 10)
+        ok = bool(torch.equal(gv, ev) and torch.equal(gs, es) and torch.equal(gf, ef))
+        q.put((rank, ok, lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [10, 11, 1])
+def test_two_rank_gather(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + n_total
+    procs = [ctx.Process(target=_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    spans = sorted((lo, hi) for _, _, lo, hi in res)
+    assert spans[0][0] == 0 and spans[-1][1] == n_total and spans[0][1] == spans[1][0]
+
+
+def test_shard_bounds_cover_everything():
+    from frenetix_occlusion_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 8, 1000, 1_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert all(0 <= hi - lo <= (n + w - 1) // w for lo, hi in spans)
