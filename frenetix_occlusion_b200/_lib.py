@@ -60,6 +60,24 @@ class FoMetricArgs(C.Structure):
                 ("pair", C.c_void_p), ("step", C.c_void_p)]
 
 
+class FoVisibilityArgs(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_rays", C.c_int32), ("n_obstacles", C.c_int32), ("n_boundary", C.c_int32),
+                ("ego", C.c_void_p), ("rect", C.c_void_p), ("rect_flags", C.c_void_p), ("boundary", C.c_void_p),
+                ("sensor_radius", C.c_float), ("sensor_angle_deg", C.c_float),
+                ("range", C.c_void_p), ("hit", C.c_void_p), ("visible", C.c_void_p)]
+
+
+class FoRolloutCvArgs(C.Structure):
+    _fields_ = [("n_agents", C.c_int32), ("n_states", C.c_int32), ("t_stride", C.c_int32), ("dt", C.c_double),
+                ("var0", C.c_double), ("var_factor", C.c_double),
+                ("x0", C.c_void_p), ("y0", C.c_void_p), ("v", C.c_void_p), ("phi", C.c_void_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("yaw", C.c_void_p), ("vel", C.c_void_p),
+                ("var_x", C.c_void_p), ("var_y", C.c_void_p)]
+
+
+HIT_NONE, HIT_BOUNDARY = -1, -2
+RECT_EXISTS, RECT_TRANSPARENT = 1, 2
+
 # every symbol include/fo_b200.h declares: name -> (restype, argtypes)
 _PROTOS = {
     "fo_agent_table_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -68,6 +86,8 @@ _PROTOS = {
     "fo_metric_bundle_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(FoAgentsRaw),
                                         C.POINTER(FoMetricArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "fo_visibility_raycast": (C.c_int, [C.POINTER(FoVisibilityArgs), C.c_void_p]),
+    "fo_rollout_cv": (C.c_int, [C.POINTER(FoRolloutCvArgs), C.c_void_p]),
     "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),
     "fo_launch_count": (C.c_uint64, []),
     "fo_version": (C.c_int, []),

@@ -1,0 +1,36 @@
+"""Host wrapper of the phantom-agent rollout kernels (stage 2)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def rollout_cv(x0, y0, v, phi, dt: float, horizon: float, var0: float = 0.1, var_factor: float = 1.05,
+               origin=(0.0, 0.0), device="cuda:0"):
+    """Constant-velocity pedestrian predictions (reference agent.py:451-536) for A agents at once.
+    Returns float32 device tensors ``x, y, yaw, v, var`` of shape [A, T], T = int(horizon/dt)+1,
+    positions relative to ``origin`` (subtracted in float64)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("frenetix_occlusion_b200 needs a CUDA device (no CPU fallback)")
+    device = torch.device(device)
+    x0 = np.atleast_1d(np.asarray(x0, dtype=np.float64)) - origin[0]
+    y0 = np.atleast_1d(np.asarray(y0, dtype=np.float64)) - origin[1]
+    v = np.atleast_1d(np.asarray(v, dtype=np.float64))
+    phi = np.atleast_1d(np.asarray(phi, dtype=np.float64))
+    A = len(x0)
+    T = int(horizon / dt) + 1
+    with torch.cuda.device(device):
+        inp = torch.from_numpy(np.stack([x0, y0, v, phi])).to(device)
+        out = torch.empty((6, A, T), dtype=torch.float32, device=device)
+        a = L.FoRolloutCvArgs()
+        a.n_agents, a.n_states, a.t_stride, a.dt = A, T, T, float(dt)
+        a.var0, a.var_factor = float(var0), float(var_factor)
+        a.x0, a.y0, a.v, a.phi = [inp[i].data_ptr() for i in range(4)]
+        a.x, a.y, a.yaw, a.vel, a.var_x, a.var_y = [out[i].data_ptr() for i in range(6)]
+        L.check(L.lib.fo_rollout_cv(C.byref(a), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                "fo_rollout_cv")
+    return {"x": out[0], "y": out[1], "yaw": out[2], "v": out[3], "var": out[4], "_keepalive": inp}

@@ -152,6 +152,56 @@ int fo_metric_bundle_host(const float *ego_host, int32_t n_traj, int32_t n_state
                           uint8_t *out_valid, float *out_summary, uint32_t *out_flags, float *out_pair,
                           float *out_step);
 
+
+/* ---- stage 1: sensor visibility by ray casting ----------------------------------------------------
+ * Replaces SensorModel.calc_visible_and_occluded_area (sensor_model.py:41-193): the reference clips
+ * road ∩ sensor-sector with one "shadow" quad per road-border edge (sensor_model.py:137-155) and per
+ * non-bicycle obstacle (sensor_model.py:174-191, helper_functions.py:139-176).  A point lies in such a
+ * shadow exactly when the segment ego->point crosses the occluding edge, so the same region is
+ * described by the first-hit range of every ray of a fan over the field of view.  F independent
+ * frames per call (frame = one ego pose + obstacle set); rays are uniform over
+ * [heading - fov/2, heading + fov/2] (fov >= 359.9 deg: full circle, angle_r = heading - pi + 2 pi r / R). */
+#define FO_HIT_NONE (-1)      /* ray reaches the sensor radius unobstructed */
+#define FO_HIT_BOUNDARY (-2)  /* first hit is a road-border segment */
+enum { FO_RECT_EXISTS = 1u << 0,        /* obstacle has a state at this time step (fo_obstacle.py:79-116) */
+       FO_RECT_TRANSPARENT = 1u << 1 }; /* obstacle type 'bicycle': seen but casts no shadow (sensor_model.py:177) */
+
+typedef struct FoVisibilityArgs {
+  int32_t n_frames, n_rays, n_obstacles, n_boundary;
+  const float *ego;            /* dev [F, 3] (x, y, heading) */
+  const float *rect;           /* dev [F, O, 5] (cx, cy, yaw, half_length, half_width): corner points as
+                                  helper_functions.py:99-112 */
+  const uint8_t *rect_flags;   /* dev [F, O] FO_RECT_* */
+  const float *boundary;       /* dev [B, 4] (x1, y1, x2, y2) opaque road-border segments, world frame,
+                                  shared by all frames; may be NULL when n_boundary == 0 */
+  float sensor_radius;         /* occlusion.yaml:36 */
+  float sensor_angle_deg;      /* occlusion.yaml:37 */
+  float *range;                /* dev [F, R] first-hit distance, <= sensor_radius */
+  int32_t *hit;                /* dev [F, R] obstacle index | FO_HIT_NONE | FO_HIT_BOUNDARY */
+  uint8_t *visible;            /* dev [F, O] 1 = some ray sees the obstacle (visible_objects_timestep,
+                                  sensor_model.py:64-76); may be NULL */
+} FoVisibilityArgs;
+
+int fo_visibility_raycast(const FoVisibilityArgs *args, void *stream);
+
+/* ---- stage 2: phantom-agent rollouts ---------------------------------------------------------------
+ * Constant-velocity pedestrian prediction: OAPPedestrianAgent._create_ped_trajectory (agent.py:451-505)
+ * + _create_cr_predictions (agent.py:520-536) + create_cov_matrix (agent.py:260-280), written straight
+ * into the SoA layout FoAgentsRaw expects.  Per agent: start (x0, y0) [double, origin-shifted by the
+ * caller], speed v and heading phi; vx = round(v cos phi, 3), vy = round(v sin phi, 3) (agent.py:492-493);
+ * pos[k] = p0 + k dt (vx, vy), yaw[k] = phi, v[k] = v, var[k] = var0 * factor^k. */
+typedef struct FoRolloutCvArgs {
+  int32_t n_agents;
+  int32_t n_states;            /* int(horizon / dt) + 1 (agent.py:496) */
+  int32_t t_stride;            /* row stride of the outputs (>= n_states) */
+  double dt;
+  double var0, var_factor;     /* 0.1 and agent_manager.prediction.variance_factor (occlusion.yaml:91) */
+  const double *x0, *y0, *v, *phi;   /* dev [A] */
+  float *x, *y, *yaw, *vel, *var_x, *var_y;   /* dev [A, t_stride] */
+} FoRolloutCvArgs;
+
+int fo_rollout_cv(const FoRolloutCvArgs *args, void *stream);
+
 /* FP32 FMA-pipe probe used by bench.py to measure the roofline denominator on the box it runs on:
  * runs `iters` dependent-chain FFMAs on every lane of a full-occupancy grid and returns elapsed
  * milliseconds (CUDA events) in *ms and the flop count in *flops. */

@@ -1,0 +1,182 @@
+"""Oracle for stage 1 (sensor visibility) and stage 2 (constant-velocity rollout).  TEST INFRASTRUCTURE.
+
+PARITY UNPINNED at the polygon level: the reference builds its visible area with shapely/GEOS
+boolean operations (``sensor_model.py:103-193``), which cannot be installed here, and ships no test
+vectors.  Two restatements are kept instead:
+
+* ``reference_point_visible``  -- the reference's own construction evaluated point-wise, polygon-library
+  free: a point is visible iff it lies in the sensor sector, in none of the per-border-edge shadow
+  quads ``[v1, v2, v2+100(v2-ego), v1+100(v1-ego)]`` (``sensor_model.py:137-155``,
+  ``helper_functions.py:79-96``) and in none of the per-obstacle shadows built from the corner pair
+  with the largest subtended angle (``helper_functions.py:139-176``) united with the obstacle itself
+  (``sensor_model.py:174-191``); bicycles cast no shadow (``sensor_model.py:177``).
+* ``raycast`` -- float64 brute-force restatement of the ray-cast formulation the CUDA kernel uses
+  (first hit of every ray of the fan), bit-for-bit the same angle convention and closed-interval
+  hit rule.  The tests check kernel == ``raycast`` (ranges to 1e-5, hit ids exactly except grazing
+  ties) and ``raycast`` == ``reference_point_visible`` up to the angular resolution of the fan.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HIT_NONE, HIT_BOUNDARY = -1, -2
+RECT_EXISTS, RECT_TRANSPARENT = 1, 2
+
+
+def ray_angles(heading: float, fov_deg: float, n_rays: int) -> np.ndarray:
+    if fov_deg >= 359.9:                                   # sensor_model.py:119-120 (full disc)
+        return heading - np.pi + 2.0 * np.pi * np.arange(n_rays) / n_rays
+    fov = np.radians(fov_deg)
+    return heading - 0.5 * fov + (fov / max(n_rays - 1, 1)) * np.arange(n_rays)
+
+
+def rect_corners(rect: np.ndarray) -> np.ndarray:
+    """[O,5] (cx, cy, yaw, hl, hw) -> [O,4,2] corner ring in commonroad ``Rectangle.vertices`` order,
+    rotated and translated as ``hf.calc_corner_points`` does (helper_functions.py:99-112)."""
+    rect = np.asarray(rect, dtype=np.float64).reshape(-1, 5)
+    sx = np.array([-1.0, -1.0, 1.0, 1.0])
+    sy = np.array([-1.0, 1.0, 1.0, -1.0])
+    lx = sx[None] * rect[:, 3:4]
+    ly = sy[None] * rect[:, 4:5]
+    c, s = np.cos(rect[:, 2:3]), np.sin(rect[:, 2:3])
+    return np.stack((rect[:, 0:1] + lx * c - ly * s, rect[:, 1:2] + lx * s + ly * c), -1)
+
+
+def _edges(ego_xy, rect, flags, boundary):
+    rect = np.asarray(rect, dtype=np.float64).reshape(-1, 5)
+    flags = np.asarray(flags).reshape(-1)
+    segs, owner = [], []
+    cor = rect_corners(rect)
+    for o in range(len(rect)):
+        if (flags[o] & RECT_EXISTS) and not (flags[o] & RECT_TRANSPARENT):
+            for e in range(4):
+                segs.append(np.concatenate((cor[o, e], cor[o, (e + 1) % 4])))
+                owner.append(o)
+    if boundary is not None and len(boundary):
+        for b in np.asarray(boundary, dtype=np.float64).reshape(-1, 4):
+            segs.append(b)
+            owner.append(HIT_BOUNDARY)
+    segs = np.asarray(segs, dtype=np.float64).reshape(-1, 4)
+    segs = segs - np.tile(np.asarray(ego_xy, dtype=np.float64), 2)
+    return segs, np.asarray(owner, dtype=np.int64)
+
+
+def raycast(ego, rect, flags, boundary, sensor_radius, fov_deg, n_rays):
+    """First-hit range / hit id per ray and per-obstacle visibility for ONE frame (float64)."""
+    ego = np.asarray(ego, dtype=np.float64)
+    ang = ray_angles(ego[2], fov_deg, n_rays)
+    c, s = np.cos(ang)[:, None], np.sin(ang)[:, None]
+    segs, owner = _edges(ego[:2], rect, flags, boundary)
+    rng = np.full(n_rays, float(sensor_radius))
+    hit = np.full(n_rays, HIT_NONE, dtype=np.int64)
+    if len(segs):
+        ax, ay = segs[None, :, 0], segs[None, :, 1]
+        ex, ey = segs[None, :, 2] - ax, segs[None, :, 3] - ay
+        D = c * ey - s * ex
+        tn = ax * ey - ay * ex
+        un = ax * s - ay * c
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = tn / D
+            u = un / D
+        ok = (D != 0) & (t >= 0) & (u >= 0) & (u <= 1) & (t < sensor_radius)
+        t = np.where(ok, t, np.inf)
+        j = t.argmin(1)
+        tb = t[np.arange(n_rays), j]
+        better = tb < rng
+        rng = np.where(better, tb, rng)
+        hit = np.where(better, owner[j], hit)
+    rect = np.asarray(rect, dtype=np.float64).reshape(-1, 5)
+    flags = np.asarray(flags).reshape(-1)
+    visible = np.zeros(len(rect), dtype=np.uint8)
+    for o in np.unique(hit[hit >= 0]):
+        visible[o] = 1
+    for o in range(len(rect)):                             # transparent obstacles: slab test up to the first hit
+        if (flags[o] & RECT_EXISTS) and (flags[o] & RECT_TRANSPARENT):
+            cx, cy, yaw, hl, hw = rect[o]
+            cx, cy = cx - ego[0], cy - ego[1]
+            cs, sn = np.cos(yaw), np.sin(yaw)
+            ox, oy = -(cx * cs + cy * sn), -(-cx * sn + cy * cs)
+            dx, dy = c[:, 0] * cs + s[:, 0] * sn, -c[:, 0] * sn + s[:, 0] * cs
+            with np.errstate(divide="ignore", invalid="ignore"):
+                tx0, tx1 = (-hl - ox) / dx, (hl - ox) / dx
+                ty0, ty1 = (-hw - oy) / dy, (hw - oy) / dy
+            t0 = np.maximum(np.minimum(tx0, tx1), np.minimum(ty0, ty1))
+            t1 = np.minimum(np.maximum(tx0, tx1), np.maximum(ty0, ty1))
+            if np.any((np.maximum(t0, 0.0) <= np.minimum(t1, rng))):
+                visible[o] = 1
+    return rng, hit, visible
+
+
+# ------------------------------------------------------------------------------------------------
+def _angle_between(v1, v2):
+    v1 = v1 / np.linalg.norm(v1)
+    v2 = v2 / np.linalg.norm(v2)
+    return np.arccos(np.clip(np.dot(v1, v2), -1.0, 1.0))
+
+
+def identify_projection_points(ego_xy, corner_points):
+    """helper_functions.py:157-176: the corner pair with the largest subtended angle (first maximum)."""
+    max_angle = 0
+    ret = (corner_points[0], corner_points[0])
+    for p1 in corner_points:
+        for p2 in corner_points:
+            a = _angle_between(p1 - ego_xy, p2 - ego_xy)
+            if a > max_angle:
+                max_angle = a
+                ret = (p1, p2)
+    return ret
+
+
+def _in_convex_quad(P, quad):
+    """Closed point-in-convex-polygon test for points [M,2]; orientation independent."""
+    q = np.asarray(quad, dtype=np.float64)
+    e = np.roll(q, -1, axis=0) - q
+    rel = P[:, None, :] - q[None]
+    cr = e[None, :, 0] * rel[..., 1] - e[None, :, 1] * rel[..., 0]
+    return np.all(cr >= 0, 1) | np.all(cr <= 0, 1)
+
+
+def reference_point_visible(P, ego, rect, flags, boundary, sensor_radius, fov_deg):
+    """Point-wise evaluation of the reference's visible-area construction (see module docstring).
+    ``boundary``: [B,4] consecutive exterior-vertex pairs (x1,y1,x2,y2) of road ∩ sector."""
+    P = np.asarray(P, dtype=np.float64).reshape(-1, 2)
+    ego = np.asarray(ego, dtype=np.float64)
+    e = ego[:2]
+    d = P - e
+    r = np.hypot(d[:, 0], d[:, 1])
+    vis = r <= sensor_radius
+    if fov_deg < 359.9:                                    # sensor_model.py:201-209 sector
+        rel = (np.arctan2(d[:, 1], d[:, 0]) - ego[2] + np.pi) % (2 * np.pi) - np.pi
+        vis &= np.abs(rel) <= np.radians(fov_deg) / 2
+    if boundary is not None:
+        for b in np.asarray(boundary, dtype=np.float64).reshape(-1, 4):
+            v1, v2 = b[:2], b[2:]
+            quad = [v1, v2, v2 + 100 * (v2 - e), v1 + 100 * (v1 - e)]   # helper_functions.py:90-94
+            vis &= ~_in_convex_quad(P, quad)
+    rect = np.asarray(rect, dtype=np.float64).reshape(-1, 5)
+    cor = rect_corners(rect)
+    for o in range(len(rect)):
+        if not (flags[o] & RECT_EXISTS) or (flags[o] & RECT_TRANSPARENT):   # sensor_model.py:177
+            continue
+        c1, c2 = identify_projection_points(e, cor[o])
+        u1 = (c1 - e) / np.linalg.norm(c1 - e)
+        u2 = (c2 - e) / np.linalg.norm(c2 - e)
+        quad = [c1, c2, c2 + u2 * 100, c1 + u1 * 100]                    # helper_functions.py:143-148
+        vis &= ~_in_convex_quad(P, quad)
+        vis &= ~_in_convex_quad(P, cor[o])                                # obstacle polygon itself
+    return vis
+
+
+# ------------------------------------------------------------------------------------------------
+def rollout_cv(x0, y0, v, phi, dt, horizon, var0=0.1, var_factor=1.05):
+    """Pedestrian constant-velocity prediction, float64, exactly the reference's arithmetic
+    (agent.py:487-503, 520-536, 260-280).  Returns dict of [A,T] arrays."""
+    x0, y0, v, phi = (np.atleast_1d(np.asarray(a, dtype=np.float64)) for a in (x0, y0, v, phi))
+    n = int(horizon / dt) + 1                                              # agent.py:496
+    vx = np.array([round(float(a), 3) for a in v * np.cos(phi)])          # agent.py:492
+    vy = np.array([round(float(a), 3) for a in v * np.sin(phi)])          # agent.py:493
+    t = np.arange(n)[None, :] * dt                                         # agent.py:499
+    k = np.arange(n)
+    return {"x": x0[:, None] + t * vx[:, None], "y": y0[:, None] + t * vy[:, None],
+            "yaw": np.repeat(phi[:, None], n, 1), "v": np.repeat(v[:, None], n, 1),
+            "var": np.repeat((var0 * np.power(var_factor, k))[None], len(v), 0)}

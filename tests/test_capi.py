@@ -1,0 +1,56 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol the header declares;
+argument validation works without touching the device."""
+import ctypes as C
+import os
+import re
+
+from conftest import ROOT
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "fo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    from frenetix_occlusion_b200 import _lib as L
+    names = _header_functions()
+    assert len(names) >= 9
+    raw = C.CDLL(L.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/fo_b200.h but not exported by libfo_b200.so"
+    assert set(names) == set(L.EXPORTED_SYMBOLS), set(names) ^ set(L.EXPORTED_SYMBOLS)
+
+
+def test_argument_validation_without_device():
+    from frenetix_occlusion_b200 import _lib as L
+    assert L.lib.fo_version() == 1
+    assert L.lib.fo_agent_table_bytes(256, 51) == 256 * 51 * 40 + 256 * 32
+    assert L.lib.fo_metric_bundle(None, None) == -1
+    assert b"NULL" in L.lib.fo_last_error()
+    a = L.FoMetricArgs()
+    a.n_traj = -3
+    assert L.lib.fo_metric_bundle(C.byref(a), None) == -1
+    a.n_traj, a.n_states = 4, 4000          # T beyond FO_MAX_STATES, pointers non-NULL
+    buf = (C.c_float * 16)()
+    a.ego = C.cast(buf, C.c_void_p)
+    a.valid = C.cast(buf, C.c_void_p)
+    assert L.lib.fo_metric_bundle(C.byref(a), None) == -2
+    v = L.FoVisibilityArgs()
+    v.n_frames, v.n_rays = 1, 8
+    assert L.lib.fo_visibility_raycast(C.byref(v), None) == -1      # NULL arrays
+    r = L.FoRolloutCvArgs()
+    r.n_agents, r.n_states, r.t_stride = 2, 31, 8
+    assert L.lib.fo_rollout_cv(C.byref(r), None) == -1              # stride < states
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from frenetix_occlusion_b200.engine import MetricEngine
+    from frenetix_occlusion_b200 import synthetic as S
+    with pytest.raises(RuntimeError):
+        MetricEngine(S.VEHICLE, 0.1, S.ALL_METRICS, S.DEFAULT_THRESHOLDS)
