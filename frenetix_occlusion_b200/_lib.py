@@ -75,6 +75,15 @@ class FoRolloutCvArgs(C.Structure):
                 ("var_x", C.c_void_p), ("var_y", C.c_void_p)]
 
 
+class FoRolloutPathArgs(C.Structure):
+    _fields_ = [("n_jobs", C.c_int32), ("n_states", C.c_int32), ("t_stride", C.c_int32), ("dt", C.c_double),
+                ("t1", C.c_double), ("var0", C.c_double), ("var_factor", C.c_double),
+                ("path_xy", C.c_void_p), ("path_off", C.c_void_p),
+                ("x0", C.c_void_p), ("y0", C.c_void_p), ("v0", C.c_void_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("yaw", C.c_void_p), ("vel", C.c_void_p),
+                ("var_x", C.c_void_p), ("var_y", C.c_void_p), ("sample", C.c_void_p)]
+
+
 HIT_NONE, HIT_BOUNDARY = -1, -2
 RECT_EXISTS, RECT_TRANSPARENT = 1, 2
 
@@ -88,6 +97,7 @@ _PROTOS = {
                                         C.c_void_p]),
     "fo_visibility_raycast": (C.c_int, [C.POINTER(FoVisibilityArgs), C.c_void_p]),
     "fo_rollout_cv": (C.c_int, [C.POINTER(FoRolloutCvArgs), C.c_void_p]),
+    "fo_rollout_path": (C.c_int, [C.POINTER(FoRolloutPathArgs), C.c_void_p]),
     "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),
     "fo_launch_count": (C.c_uint64, []),
     "fo_version": (C.c_int, []),

@@ -1,0 +1,265 @@
+"""Agent manager and phantom/real agents (mirror of reference agent.py:27-537).
+
+Same public surface (``FOAgentManager.add_agent / reset / update_real_agents /
+agent_by_prediction_id``, ``predictions`` dict in the reference's layout, id scheme
+``int(str(agent_id) + str(i))``); the rollouts run in the CUDA kernels ``fo_rollout_cv`` /
+``fo_rollout_path``.  Predictions are brought back to the host as float64 numpy arrays because the
+reference's plugin protocol hands them to arbitrary user metrics; the dense core re-uploads them once
+per planning cycle (a few kB)."""
+from __future__ import annotations
+
+import types
+from random import randint
+
+import numpy as np
+import torch
+
+from .prediction import rollout_cv, rollout_path
+from .route_planner import FORoutePlanner
+from .scenario import Obstacle, Rectangle, State
+
+
+def calc_normal_vector_to_curve(curve, pos):
+    """helper_functions.py:38-57: unit vector from ``pos`` to the closest point of the polyline."""
+    c = np.asarray(curve, dtype=np.float64)
+    pos = np.asarray(pos, dtype=np.float64)
+    seg = c[1:] - c[:-1]
+    l2 = np.maximum((seg ** 2).sum(1), 1e-18)
+    u = np.clip(((pos - c[:-1]) * seg).sum(1) / l2, 0.0, 1.0)
+    q = c[:-1] + u[:, None] * seg
+    j = int(np.argmin(np.hypot(*(pos - q).T)))
+    v = q[j] - pos
+    return v / np.linalg.norm(v)
+
+
+def angle_between_positive(v1, v2):
+    """helper_functions.py:60-69."""
+    v1 = np.asarray(v1, dtype=np.float64) / np.linalg.norm(v1)
+    v2 = np.asarray(v2, dtype=np.float64) / np.linalg.norm(v2)
+    a = np.arctan2(v1[0] * v2[1] - v1[1] * v2[0], float(np.dot(v1, v2)))
+    return a + 2 * np.pi if a < 0 else a
+
+
+class OAPAgent:
+    def __init__(self, pos, velocity, agent_type, agent_params, scenario, config, dt=0.1, horizon=3.0,
+                 visualization=None, debug=False, device="cuda:0"):
+        self.cr_scenario = scenario
+        self.dt = dt
+        self.horizon = horizon
+        self.agent_id = agent_params["agent_id"]
+        self.visualization = visualization
+        self.debug = debug
+        self.initial_position = np.asarray(pos, dtype=np.float64)
+        self.initial_velocity = velocity
+        self.agent_type = agent_type
+        self.obstacle_type = types.SimpleNamespace(value=agent_type.lower(), name=agent_type.upper())
+        self.agent_params = agent_params
+        self.shape = Rectangle(agent_params["length"], agent_params["width"], center=np.array([0.0, 0.0]), orientation=0.0)
+        self.initial_state = None
+        self.predictions = None
+        self.config = config
+        self.device = device
+        self.commonroad_dynamic_obstacle = None
+
+    def _buffered_shape(self):
+        """agent.py:402-407 / 525-526: Bicycle uses the *_l factors, everything else *_s."""
+        p = self.config["prediction"]
+        if self.agent_type == "Bicycle":
+            return {"length": self.shape.length * p["size_factor_length_l"], "width": self.shape.width * p["size_factor_width_l"]}
+        return {"length": self.shape.length * p["size_factor_length_s"], "width": self.shape.width * p["size_factor_width_s"]}
+
+    def _prediction_dict(self, ro, j, n):
+        x, y = ro["x"][j, :n].cpu().numpy().astype(np.float64), ro["y"][j, :n].cpu().numpy().astype(np.float64)
+        var = ro["var"][j, :n].cpu().numpy().astype(np.float64)
+        return {"orientation_list": ro["yaw"][j, :n].cpu().numpy().astype(np.float64),
+                "v_list": ro["v"][j, :n].cpu().numpy().astype(np.float64),
+                "pos_list": np.column_stack((x, y)), "shape": self._buffered_shape(),
+                "cov_list": np.array([[[v, 0.0], [0.0, v]] for v in var])}
+
+    def add_to_commonroad_scenario(self, timestep=0):
+        """agent.py:225-252: the agent becomes a dynamic obstacle whose trajectory starts at timestep + 1."""
+        pred = self._full_prediction
+        init = State(position=self.initial_state.position, orientation=self.initial_state.orientation,
+                     velocity=self.initial_state.velocity, time_step=timestep)
+        states = [State(position=pred["pos_list"][i], orientation=pred["orientation_list"][i],
+                        velocity=pred["v_list"][i], time_step=timestep + i) for i in range(1, len(pred["pos_list"]))]
+        self.commonroad_dynamic_obstacle = Obstacle(self.agent_id, self.agent_type.lower(), "dynamic", self.shape, init, states)
+        self.cr_scenario.add_objects(self.commonroad_dynamic_obstacle)
+
+
+class OAPPedestrianAgent(OAPAgent):
+    def __init__(self, pos, velocity, agent_type, agent_params, scenario, config, dt=0.1, horizon=3.0, ref_path=None,
+                 visualization=None, debug=False, mode="ref_path", orientation=None, device="cuda:0"):
+        super().__init__(pos, velocity, agent_type, agent_params, scenario, config, dt, horizon, visualization, debug, device)
+        self.ego_reference_path = ref_path
+        self.reference_curve = None
+        phi = self._initial_orientation(mode, orientation)
+        self.initial_state = State(position=self.initial_position, orientation=phi, velocity=self.initial_velocity, time_step=0)
+        # constant-velocity rollout on the device (agent.py:487-503)
+        vf = config["prediction"]["variance_factor"]
+        ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], dt, horizon, 0.1, vf, device=device)
+        torch.cuda.current_stream(torch.device(device)).synchronize()
+        n = int(horizon / dt) + 1
+        self._full_prediction = self._prediction_dict(ro, 0, n)
+        self.trajectory = self._full_prediction["pos_list"]
+        self.predictions = self._create_cr_predictions(0)
+
+    def _initial_orientation(self, mode, orientation):
+        """agent.py:453-484: towards the lane centre / the ego reference path unless the spawn point fixes it."""
+        if mode == "lane_center":
+            ids = self.cr_scenario.lanelet_network.find_lanelet_by_position([self.initial_position])[0]
+            curve = np.array(self.cr_scenario.lanelet_network.find_lanelet_by_id(ids[0]).center_vertices) if ids \
+                else self.ego_reference_path            # (the reference falls through to None here, agent.py:463-465)
+        elif mode == "ref_path":
+            curve = self.ego_reference_path
+        else:
+            raise NotImplementedError(f'Selected mode "{mode}" is not implemented: use "ref_path" or "lane_center"!')
+        if orientation is not None:
+            return float(orientation)
+        self.reference_curve = curve
+        return float(angle_between_positive(np.array([1, 0]), calc_normal_vector_to_curve(curve, self.initial_position)))
+
+    def _create_cr_predictions(self, timestep) -> list:
+        p = self._full_prediction
+        return [{"orientation_list": p["orientation_list"][timestep:], "v_list": p["v_list"][timestep:],
+                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"], "cov_list": p["cov_list"][timestep:]}]
+
+
+class OAPVehicleAgent(OAPAgent):
+    def __init__(self, pos, velocity, agent_type, agent_params, scenario, config, dt=0.1, horizon=3.0,
+                 visualization=None, debug=False, device="cuda:0"):
+        super().__init__(pos, velocity, agent_type, agent_params, scenario, config, dt, horizon, visualization, debug, device)
+        self.route_planner = FORoutePlanner(scenario, scenario.lanelet_network, visualization, debug)
+        self.reference_paths = self.route_planner.calc_possible_reference_paths(pos)
+        self.initial_state = State(position=self.initial_position, orientation=self.route_planner.lanelet_orientation,
+                                   velocity=self.initial_velocity, time_step=0)
+        vf = config["prediction"]["variance_factor"]
+        J = len(self.reference_paths)
+        ro = rollout_path(self.reference_paths, [pos[0]] * J, [pos[1]] * J, [velocity] * J, dt, horizon, 3.0, 0.1, vf,
+                          device=device)
+        torch.cuda.current_stream(torch.device(device)).synchronize()
+        n = int(horizon / dt) + 1
+        smp = ro["sample"].cpu().numpy()
+        self._all_predictions = [self._prediction_dict(ro, j, n) for j in range(J) if smp[j] >= 0]
+        self._full_prediction = self._all_predictions[0] if self._all_predictions else None
+        self.predictions = self._create_cr_predictions(0)
+
+    def _create_cr_predictions(self, timestep) -> list:
+        """agent.py:398-426: one prediction per route reference path."""
+        return [{"orientation_list": p["orientation_list"][timestep:], "v_list": p["v_list"][timestep:],
+                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"], "cov_list": p["cov_list"][timestep:]}
+                for p in self._all_predictions]
+
+    @staticmethod
+    def get_lanelet_velocity(pos, scenario):
+        raise NotImplementedError("velocity='lanelet' needs traffic-sign interpretation (commonroad); pass a number")
+
+
+class FOAgentManager:
+    def __init__(self, scenario, reference_path, config, timestep, visualization=None, dt=0.1, fo_obstacles=None,
+                 debug=False, device="cuda:0"):
+        self.scenario = scenario
+        self.timestep = timestep
+        self.reference_path = reference_path
+        self.config = config
+        self.visualization = visualization
+        self.fo_obstacles = fo_obstacles
+        self.dt = dt
+        self.debug = debug
+        self.device = device
+        self.phantom_agents = []
+        self.real_agents = []
+        self.predictions = {}
+        self.version = 0
+        self._get_all_ids()
+
+    def reset(self):
+        self.phantom_agents = []
+        self.predictions = {}
+        self.version += 1
+
+    _PARAMS = {"bicycle": ("Bicycle", 4, 11.5), "car": ("Car", 7.32, 11.5), "truck": ("Truck", 7.32, 7)}
+
+    def add_agent(self, pos, velocity="default", agent_type="Car", add_to_scenario=False, timestep=0, horizon=3.0,
+                  mode="ref_path", orientation=None):
+        """agent.py:48-157 (same defaults, same errors)."""
+        if self.timestep != timestep:
+            return
+        agent_id = self._create_id()
+        key = agent_type.lower()
+        if key in self._PARAMS:
+            conf = self.config[key]
+            name, sw, amax = self._PARAMS[key]
+            agent_params = {"agent_id": agent_id, "type": name, "width": conf["width"], "length": conf["length"],
+                            "delta_max": 1.066, "wheelbase": conf["wheelbase"], "switching_velocity": sw,
+                            "max_acceleration": amax, "velocity_delta_max": 0.4}
+            if velocity == "default":
+                velocity = conf["default_velocity"]
+            elif velocity == "lanelet":
+                if key == "bicycle":
+                    raise NotImplementedError
+                velocity = OAPVehicleAgent.get_lanelet_velocity(pos=pos, scenario=self.scenario)
+            elif not isinstance(velocity, (float, int)):
+                raise ValueError('Only "default", "lanelet", int or float is allowed!')
+        elif key == "pedestrian":
+            conf = self.config["pedestrian"]
+            agent_params = {"agent_id": agent_id, "type": "Pedestrian", "width": conf["width"], "length": conf["length"]}
+        else:
+            raise NotImplementedError(f'OAPManager: Agent type "{agent_type}" is not implemented!')
+
+        if agent_type == "Pedestrian":
+            if velocity == "default":
+                velocity = conf["default_velocity"]
+            elif velocity == "lanelet":
+                raise NotImplementedError
+            elif not isinstance(velocity, (float, int)):
+                raise ValueError('Only "default", int or float is allowed!')
+            agent = OAPPedestrianAgent(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
+                                       scenario=self.scenario, dt=self.dt, horizon=horizon, ref_path=self.reference_path,
+                                       visualization=self.visualization, debug=self.debug, mode=mode,
+                                       orientation=orientation, config=self.config, device=self.device)
+        else:
+            agent = OAPVehicleAgent(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
+                                    scenario=self.scenario, dt=self.dt, horizon=horizon, visualization=self.visualization,
+                                    debug=self.debug, config=self.config, device=self.device)
+        if add_to_scenario:
+            self.real_agents.append(agent)
+            agent.add_to_commonroad_scenario(timestep=timestep)
+            if self.fo_obstacles is not None:
+                self.fo_obstacles.add(agent.commonroad_dynamic_obstacle)
+        else:
+            self.phantom_agents.append(agent)
+            self._add_prediction(agent)
+        return agent
+
+    def agent_by_prediction_id(self, prediction_id):
+        if not self.phantom_agents:
+            return
+        agent_id = int(str(prediction_id)[:5])
+        for agent in self.phantom_agents:
+            if agent.agent_id == agent_id:
+                return agent
+
+    def update_real_agents(self, cr_scenario_predictions):
+        """agent.py:171-177: overwrite the planner's prediction of real pedestrians (mutates the caller's dict)."""
+        for agent in self.real_agents:
+            if agent.agent_type.lower() == "pedestrian":
+                if agent.agent_id in cr_scenario_predictions:
+                    agent.predictions = agent._create_cr_predictions(self.timestep)
+                    cr_scenario_predictions[agent.agent_id] = agent.predictions[0]
+
+    def _add_prediction(self, agent):
+        for i, prediction in enumerate(agent.predictions):
+            self.predictions[int(str(agent.agent_id) + str(i))] = prediction
+        self.version += 1
+
+    def _get_all_ids(self):
+        self.all_obstacle_id = [o.obstacle_id for o in self.scenario.obstacles]
+
+    def _create_id(self):
+        agent_id = randint(10000, 11000)
+        if agent_id in self.all_obstacle_id:
+            agent_id = self._create_id()
+        else:
+            self.all_obstacle_id.append(agent_id)
+        return agent_id

@@ -202,6 +202,29 @@ typedef struct FoRolloutCvArgs {
 
 int fo_rollout_cv(const FoRolloutCvArgs *args, void *stream);
 
+/* Path-following vehicle prediction (Car / Bicycle / Truck phantoms and configured real agents):
+ * replaces OAPVehicleAgent (agent.py:283-426) + FrenetixHandler.create_trajectories
+ * (utils/frenetix_handler.py:66-125), whose arithmetic lives in the un-vendored C++ `frenetix` library
+ * (PARITY UNPINNED).  One job per (agent, route reference path).  Per job the 3 x 3 Frenet
+ * samples of the reference are rolled out -- longitudinal quartic from (s0, v0, 0) to speed
+ * {0.8, 1.0, 1.2} * v0 with zero end acceleration at t1, lateral quintic from (d0, 0, 0) to offset
+ * {-0.5, 0, +0.5} m at t1 (frenetix_handler.py:80-105) -- mapped to Cartesian along the polyline, and the
+ * sample with the smallest variance of the Cartesian speed is kept (agent.py:364-375). */
+typedef struct FoRolloutPathArgs {
+  int32_t n_jobs;
+  int32_t n_states;            /* int(horizon / dt) + 1 */
+  int32_t t_stride;
+  double dt, t1;               /* t1 = 3.0 (frenetix_handler.py:80) */
+  double var0, var_factor;
+  const float *path_xy;        /* dev [P_total, 2] reference polylines of all jobs, concatenated */
+  const int32_t *path_off;     /* dev [n_jobs + 1] offsets into path_xy (each path: 2..1024 points) */
+  const double *x0, *y0, *v0;  /* dev [n_jobs] initial position and speed */
+  float *x, *y, *yaw, *vel, *var_x, *var_y;   /* dev [n_jobs, t_stride] */
+  int32_t *sample;             /* dev [n_jobs] selected sample 0..8 (speed-major), -1 = no valid projection */
+} FoRolloutPathArgs;
+
+int fo_rollout_path(const FoRolloutPathArgs *args, void *stream);
+
 /* FP32 FMA-pipe probe used by bench.py to measure the roofline denominator on the box it runs on:
  * runs `iters` dependent-chain FFMAs on every lane of a full-occupancy grid and returns elapsed
  * milliseconds (CUDA events) in *ms and the flop count in *flops. */

@@ -180,3 +180,69 @@ def rollout_cv(x0, y0, v, phi, dt, horizon, var0=0.1, var_factor=1.05):
     return {"x": x0[:, None] + t * vx[:, None], "y": y0[:, None] + t * vy[:, None],
             "yaw": np.repeat(phi[:, None], n, 1), "v": np.repeat(v[:, None], n, 1),
             "var": np.repeat((var0 * np.power(var_factor, k))[None], len(v), 0)}
+
+
+def rollout_path(path, x0, y0, v0, dt, horizon, t1=3.0, var0=0.1, var_factor=1.05):
+    """float64 restatement of the path-following vehicle rollout for ONE reference polyline
+    (agent.py:364-426 + utils/frenetix_handler.py:66-125; the C++ frenetix arithmetic is restated from
+    the published Werling quartic/quintic scheme -- PARITY UNPINNED).  ``path`` is rounded to float32
+    like the kernel input.  Returns dict of [T] arrays and the selected sample index."""
+    pts = np.asarray(path, dtype=np.float64).astype(np.float32).astype(np.float64).reshape(-1, 2)
+    seg = np.diff(pts, axis=0)
+    ln = np.hypot(seg[:, 0], seg[:, 1])
+    cum = np.concatenate(([0.0], np.cumsum(ln)))
+    n = len(pts)
+    # projection
+    best = (np.inf, 0.0, 0.0)
+    for j in range(n - 1):
+        if ln[j] <= 0:
+            continue
+        u = ((x0 - pts[j, 0]) * seg[j, 0] + (y0 - pts[j, 1]) * seg[j, 1]) / ln[j] ** 2
+        uc = u if ((j == 0 and u < 0) or (j == n - 2 and u > 1)) else min(max(u, 0.0), 1.0)
+        q = pts[j] + uc * seg[j]
+        dist = np.hypot(x0 - q[0], y0 - q[1])
+        if dist < best[0]:
+            best = (dist, cum[j] + uc * ln[j], (seg[j, 0] * (y0 - pts[j, 1]) - seg[j, 1] * (x0 - pts[j, 0])) / ln[j])
+    s0, d0 = best[1], best[2]
+    T = int(horizon / dt) + 1
+    t = np.arange(T) * dt
+    head = np.arctan2(seg[:, 1], seg[:, 0])
+
+    def frenet(sd1, d1):
+        a3, a4 = (sd1 - v0) / t1 ** 2, (v0 - sd1) / (2 * t1 ** 3)
+        tc = np.minimum(t, t1)
+        s = s0 + v0 * tc + a3 * tc ** 3 + a4 * tc ** 4 + np.where(t > t1, sd1 * (t - t1), 0.0)
+        sd = np.where(t < t1, v0 + 3 * a3 * tc ** 2 + 4 * a4 * tc ** 3, sd1)
+        tau = tc / t1
+        d = np.where(t < t1, d0 + (d1 - d0) * (10 * tau ** 3 - 15 * tau ** 4 + 6 * tau ** 5), d1)
+        dd = np.where(t < t1, (d1 - d0) / t1 * (30 * tau ** 2 - 60 * tau ** 3 + 30 * tau ** 4), 0.0)
+        return s, sd, d, dd
+
+    def lookup(s):
+        j = np.clip(np.searchsorted(cum, s, side="right") - 1, 0, n - 2)
+        kap = np.zeros_like(s)
+        ok = j + 2 < n
+        jj = np.where(ok, j, 0)
+        dh = head[np.minimum(jj + 1, n - 2)] - head[jj]
+        dh -= 2 * np.pi * np.rint(dh / (2 * np.pi))
+        kap = np.where(ok, dh / (0.5 * (cum[np.minimum(jj + 2, n - 1)] - cum[jj])), 0.0)
+        return j, kap
+
+    best_k, best_var, keep = 0, np.inf, None
+    for smp in range(9):
+        sd1, d1 = v0 * (0.8 + 0.2 * (smp // 3)), -0.5 + 0.5 * (smp % 3)
+        s, sd, d, dd = frenet(sd1, d1)
+        j, kap = lookup(s)
+        vl = sd * (1 - kap * d)
+        v = np.sqrt(vl ** 2 + dd ** 2)
+        var = max(np.mean(v * v) - np.mean(v) ** 2, 0.0)
+        if var < best_var - 1e-15:
+            best_k, best_var, keep = smp, var, (s, sd, d, dd, j, kap, vl, v)
+    s, sd, d, dd, j, kap, vl, v = keep
+    l = np.maximum(cum[j + 1] - cum[j], 1e-12)
+    u = (s - cum[j]) / l
+    tx, ty = seg[j, 0] / l, seg[j, 1] / l
+    k = np.arange(T)
+    return {"x": pts[j, 0] + u * seg[j, 0] - d * ty, "y": pts[j, 1] + u * seg[j, 1] + d * tx,
+            "yaw": np.arctan2(ty, tx) + np.arctan2(dd, vl), "v": v, "var": var0 * np.power(var_factor, k),
+            "sample": best_k, "s0": s0, "d0": d0}

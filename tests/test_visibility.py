@@ -116,3 +116,46 @@ def test_cuda_rollout_cv_matches_oracle(cuda_device):
             g = r[key].cpu().numpy()
             assert g.shape == o[key].shape
             assert np.array_equal(g, o[key].astype(np.float32)), key     # correctly rounded image of the float64 values
+
+
+def _arc_path(radius, n=200, length=120.0):
+    s = np.linspace(0, length, n)
+    return np.stack((radius * np.sin(s / radius), radius * (1 - np.cos(s / radius))), -1)
+
+
+def test_path_rollout_oracle_invariants():
+    """Invariants that hold regardless of the un-vendored frenetix arithmetic: on a straight path with zero
+    lateral offset the constant-speed, d1 = 0 sample has zero speed variance and reproduces CV exactly."""
+    path = np.stack((np.linspace(-10, 100, 56), np.zeros(56)), -1)
+    r = VO.rollout_path(path, 5.0, 0.0, 10.0, 0.1, 3.0)
+    assert r["sample"] == 4                                   # speed factor 1.0, d1 = 0
+    assert np.allclose(r["x"], 5.0 + 10.0 * np.arange(31) * 0.1, atol=1e-9) and np.allclose(r["y"], 0.0, atol=1e-12)
+    assert np.allclose(r["v"], 10.0) and np.allclose(r["yaw"], 0.0)
+    # lateral offset 0.4 m: nearest target offset is +0.5, speed stays ~constant, ends at d = 0.5
+    r = VO.rollout_path(path, 5.0, 0.4, 10.0, 0.1, 3.0)
+    assert r["sample"] == 5 and abs(r["y"][-1] - 0.5) < 1e-9 and abs(r["d0"] - 0.4) < 1e-12
+    # circular arc: radius preserved for d = 0
+    arc = _arc_path(40.0)
+    r = VO.rollout_path(arc, arc[10, 0], arc[10, 1], 8.0, 0.1, 3.0)
+    rad = np.hypot(r["x"], r["y"] - 40.0)
+    assert np.all(np.abs(rad - 40.0) < 0.01)
+
+
+@pytest.mark.gpu
+def test_cuda_path_rollout_matches_oracle(cuda_device):
+    from frenetix_occlusion_b200.prediction import rollout_path
+    import torch
+    rng = np.random.default_rng(8)
+    paths = [np.stack((np.linspace(-10, 100, 56), np.zeros(56)), -1), _arc_path(40.0), _arc_path(-25.0, 300, 150.0),
+             np.stack((np.linspace(0, 60, 31), 3.0 * np.sin(np.linspace(0, 60, 31) / 9.0)), -1)]
+    x0 = [5.0, 9.0, 3.0, 12.0]
+    y0 = [0.4, 1.5, -0.3, 2.2]
+    v0 = [10.0, 8.0, 5.0, 10.0]
+    for horizon in (3.0, 5.0):
+        g = rollout_path(paths, x0, y0, v0, 0.1, horizon)
+        torch.cuda.synchronize()
+        for j, p in enumerate(paths):
+            o = VO.rollout_path(p, x0[j], y0[j], v0[j], 0.1, horizon)
+            assert int(g["sample"][j]) == o["sample"], (j, int(g["sample"][j]), o["sample"])
+            for key in ("x", "y", "yaw", "v", "var"):
+                np.testing.assert_allclose(g[key][j].cpu().numpy(), o[key], rtol=2e-6, atol=2e-5, err_msg=f"{key} job {j}")
