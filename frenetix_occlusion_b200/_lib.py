@@ -67,6 +67,15 @@ class FoVisibilityArgs(C.Structure):
                 ("range", C.c_void_p), ("hit", C.c_void_p), ("visible", C.c_void_p)]
 
 
+class FoPointQueryArgs(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("n_obstacles", C.c_int32), ("n_boundary", C.c_int32), ("n_polygons", C.c_int32),
+                ("ego", C.c_void_p), ("points", C.c_void_p), ("rect", C.c_void_p), ("rect_flags", C.c_void_p),
+                ("boundary", C.c_void_p), ("poly_xy", C.c_void_p), ("poly_off", C.c_void_p),
+                ("sensor_radius", C.c_float), ("sensor_angle_deg", C.c_float), ("occluded_radius", C.c_float),
+                ("focus_obstacle", C.c_int32),
+                ("flags", C.c_void_p), ("blocker", C.c_void_p), ("lanelets", C.c_void_p)]
+
+
 class FoRolloutCvArgs(C.Structure):
     _fields_ = [("n_agents", C.c_int32), ("n_states", C.c_int32), ("t_stride", C.c_int32), ("dt", C.c_double),
                 ("var0", C.c_double), ("var_factor", C.c_double),
@@ -86,6 +95,7 @@ class FoRolloutPathArgs(C.Structure):
 
 HIT_NONE, HIT_BOUNDARY = -1, -2
 RECT_EXISTS, RECT_TRANSPARENT = 1, 2
+PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/fo_b200.h declares: name -> (restype, argtypes)
 _PROTOS = {
@@ -96,6 +106,7 @@ _PROTOS = {
                                         C.POINTER(FoMetricArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "fo_visibility_raycast": (C.c_int, [C.POINTER(FoVisibilityArgs), C.c_void_p]),
+    "fo_visibility_points": (C.c_int, [C.POINTER(FoPointQueryArgs), C.c_void_p]),
     "fo_rollout_cv": (C.c_int, [C.POINTER(FoRolloutCvArgs), C.c_void_p]),
     "fo_rollout_path": (C.c_int, [C.POINTER(FoRolloutPathArgs), C.c_void_p]),
     "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),

@@ -68,11 +68,25 @@ class OAPAgent:
             return {"length": self.shape.length * p["size_factor_length_l"], "width": self.shape.width * p["size_factor_width_l"]}
         return {"length": self.shape.length * p["size_factor_length_s"], "width": self.shape.width * p["size_factor_width_s"]}
 
+    # ---- device calls (the only places the agents touch the C ABI); host float64 arrays come back -------------
+    def _rollout_cv(self, pos, velocity, phi, var_factor):
+        ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], self.dt, self.horizon, 0.1, var_factor, device=self.device)
+        torch.cuda.current_stream(torch.device(self.device)).synchronize()
+        return {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
+
+    def _rollout_path(self, paths, pos, velocity, var_factor):
+        J = len(paths)
+        ro = rollout_path(paths, [pos[0]] * J, [pos[1]] * J, [velocity] * J, self.dt, self.horizon, 3.0, 0.1, var_factor,
+                          device=self.device)
+        torch.cuda.current_stream(torch.device(self.device)).synchronize()
+        out = {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
+        out["sample"] = ro["sample"].cpu().numpy()
+        return out
+
     def _prediction_dict(self, ro, j, n):
-        x, y = ro["x"][j, :n].cpu().numpy().astype(np.float64), ro["y"][j, :n].cpu().numpy().astype(np.float64)
-        var = ro["var"][j, :n].cpu().numpy().astype(np.float64)
-        return {"orientation_list": ro["yaw"][j, :n].cpu().numpy().astype(np.float64),
-                "v_list": ro["v"][j, :n].cpu().numpy().astype(np.float64),
+        x, y = ro["x"][j, :n], ro["y"][j, :n]
+        var = ro["var"][j, :n]
+        return {"orientation_list": np.array(ro["yaw"][j, :n]), "v_list": np.array(ro["v"][j, :n]),
                 "pos_list": np.column_stack((x, y)), "shape": self._buffered_shape(),
                 "cov_list": np.array([[[v, 0.0], [0.0, v]] for v in var])}
 
@@ -97,8 +111,7 @@ class OAPPedestrianAgent(OAPAgent):
         self.initial_state = State(position=self.initial_position, orientation=phi, velocity=self.initial_velocity, time_step=0)
         # constant-velocity rollout on the device (agent.py:487-503)
         vf = config["prediction"]["variance_factor"]
-        ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], dt, horizon, 0.1, vf, device=device)
-        torch.cuda.current_stream(torch.device(device)).synchronize()
+        ro = self._rollout_cv(pos, velocity, phi, vf)
         n = int(horizon / dt) + 1
         self._full_prediction = self._prediction_dict(ro, 0, n)
         self.trajectory = self._full_prediction["pos_list"]
@@ -135,11 +148,9 @@ class OAPVehicleAgent(OAPAgent):
                                    velocity=self.initial_velocity, time_step=0)
         vf = config["prediction"]["variance_factor"]
         J = len(self.reference_paths)
-        ro = rollout_path(self.reference_paths, [pos[0]] * J, [pos[1]] * J, [velocity] * J, dt, horizon, 3.0, 0.1, vf,
-                          device=device)
-        torch.cuda.current_stream(torch.device(device)).synchronize()
+        ro = self._rollout_path(self.reference_paths, pos, velocity, vf)
         n = int(horizon / dt) + 1
-        smp = ro["sample"].cpu().numpy()
+        smp = ro["sample"]
         self._all_predictions = [self._prediction_dict(ro, j, n) for j in range(J) if smp[j] >= 0]
         self._full_prediction = self._all_predictions[0] if self._all_predictions else None
         self.predictions = self._create_cr_predictions(0)
@@ -156,6 +167,9 @@ class OAPVehicleAgent(OAPAgent):
 
 
 class FOAgentManager:
+    pedestrian_cls = OAPPedestrianAgent
+    vehicle_cls = OAPVehicleAgent
+
     def __init__(self, scenario, reference_path, config, timestep, visualization=None, dt=0.1, fo_obstacles=None,
                  debug=False, device="cuda:0"):
         self.scenario = scenario
@@ -214,12 +228,12 @@ class FOAgentManager:
                 raise NotImplementedError
             elif not isinstance(velocity, (float, int)):
                 raise ValueError('Only "default", int or float is allowed!')
-            agent = OAPPedestrianAgent(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
+            agent = self.pedestrian_cls(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
                                        scenario=self.scenario, dt=self.dt, horizon=horizon, ref_path=self.reference_path,
                                        visualization=self.visualization, debug=self.debug, mode=mode,
                                        orientation=orientation, config=self.config, device=self.device)
         else:
-            agent = OAPVehicleAgent(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
+            agent = self.vehicle_cls(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
                                     scenario=self.scenario, dt=self.dt, horizon=horizon, visualization=self.visualization,
                                     debug=self.debug, config=self.config, device=self.device)
         if add_to_scenario:

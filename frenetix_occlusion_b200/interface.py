@@ -1,0 +1,146 @@
+"""Entry point of the assessment hot path (mirror of reference frenetix_occlusion/interface.py:18-238).
+
+Same constructor, attributes and the three calls the planner makes -- ``evaluate_scenario`` once per planning
+cycle, ``trajectory_safety_assessment`` per candidate trajectory -- plus the batched
+``assess_bundle(trajectories[N,T,5])`` that evaluates the planner's whole sampled bundle in one launch of the
+dense CUDA core (the call a planner should prefer; the per-trajectory call is one 1-trajectory launch).
+
+Differences from the reference, all at its edges: ``config_path=None`` loads the package default instead of
+crashing (interface.py:231-236 opens an unbound name); the debug visualisation is optional and never forces a
+matplotlib backend; ``evaluate_scenario`` returns the visible area as a region object over the ray-cast map
+instead of a shapely polygon."""
+from __future__ import annotations
+
+import os
+
+import yaml
+
+from .agent import FOAgentManager
+from .metrics.metric import Metric
+from .sensor_model import SensorModel
+from .spawn_locator import SpawnLocator
+from .utils.fo_obstacle import FOObstacles
+
+
+class FOInterface:
+    def __init__(self, scenario, reference_path, vehicle_params, dt, config_path=None, cosy_cl=None, device="cuda:0",
+                 visualization=None):
+        self.config = self._load_config(config_path)
+        self.cr_scenario = scenario
+        self.lanelet_network = scenario.lanelet_network
+        self.ego_reference_path = reference_path
+        self.cosy_cl = cosy_cl
+        self.vehicle_params = vehicle_params
+        self.dt = dt
+        self.plot = self.config["plot"]
+        self.debug = self.config["debug"]
+        self.device = device
+
+        self.predictions = None
+        self.ego_pos = None
+        self.ego_orientation = None
+        self.ego_pos_cl = None
+        self.timestep = None
+        self.spawn_points = []
+
+        self.sensor_radius = self.config["sensor_model"]["sensor_radius"]
+        self.sensor_angle = self.config["sensor_model"]["sensor_angle"]
+
+        # the reference constructs its matplotlib visualisation unconditionally (interface.py:97); here it is an
+        # optional object with the same drawing methods
+        self.visualization = visualization
+
+        self.fo_obstacles = FOObstacles(self.cr_scenario.obstacles)
+        self.sensor_model = self._make_sensor_model()
+        self.agent_manager = self._make_agent_manager()
+        self.spawn_locator = SpawnLocator(agent_manager=self.agent_manager, ref_path=self.ego_reference_path,
+                                          config=self.config, cosy_cl=self.cosy_cl, sensor_model=self.sensor_model,
+                                          fo_obstacles=self.fo_obstacles, visualization=self.visualization,
+                                          debug=self.debug)
+        self.metrics = self._make_metrics()
+
+    # construction hooks (one per device-backed component)
+    def _make_sensor_model(self):
+        return SensorModel(lanelet_network=self.lanelet_network, ref_path=self.ego_reference_path,
+                           sensor_radius=self.sensor_radius, sensor_angle=self.sensor_angle,
+                           visualization=self.visualization, debug=self.debug, device=self.device)
+
+    def _make_agent_manager(self):
+        return FOAgentManager(scenario=self.cr_scenario, reference_path=self.ego_reference_path,
+                              config=self.config["agent_manager"], visualization=self.visualization,
+                              timestep=self.timestep, dt=self.dt, debug=self.debug, fo_obstacles=self.fo_obstacles,
+                              device=self.device)
+
+    def _make_metrics(self):
+        return Metric(self.config["metrics"], self.vehicle_params, self.agent_manager, device=self.device)
+
+    def set_coordinate_system(self, cosy_cl):
+        self.cosy_cl = cosy_cl
+        self.spawn_locator.cosy_cl = cosy_cl
+
+    def _add_real_agents(self):
+        """interface.py:137-146: configured real agents enter the scenario at their own time step."""
+        if self.config["agents"] is None:
+            return
+        for agent in self.config["agents"]:
+            self.agent_manager.add_agent(pos=agent["position"], velocity=agent["velocity"], agent_type=agent["agent_type"],
+                                         add_to_scenario=True, timestep=agent["timestep"], horizon=agent["horizon"])
+
+    def evaluate_scenario(self, predictions, ego_pos, ego_orientation, ego_pos_cl, ego_v, timestep, cosy_cl):
+        """interface.py:148-214: visibility -> spawn points -> phantom agents (+ their predictions)."""
+        self.set_coordinate_system(cosy_cl)
+        self._update_time_step(timestep)
+        self._add_real_agents()
+        self.predictions = predictions
+        self.ego_pos = ego_pos
+        self.ego_orientation = ego_orientation
+        self.ego_pos_cl = ego_pos_cl
+        self.agent_manager.reset()
+        self.spawn_points.clear()
+        if self.visualization is not None and self.plot:
+            self.visualization.draw_scenario(timestep=self.timestep)
+            self.visualization.show_plot()
+        self.fo_obstacles.update(self.timestep)
+        self.sensor_model.calc_visible_and_occluded_area(timestep=self.timestep, ego_pos=self.ego_pos,
+                                                         ego_orientation=self.ego_orientation, obstacles=self.fo_obstacles)
+        self.fo_obstacles.update_multipolygon()
+        self.spawn_points = self.spawn_locator.find_spawn_points(self.ego_pos, self.ego_orientation, self.ego_pos_cl, ego_v)
+        for sp in self.spawn_points:
+            mode = "lane_center" if sp.source == "left turn" or sp.source == "right turn" else "ref_path"
+            self.agent_manager.add_agent(pos=sp.position, velocity="default", agent_type=sp.agent_type,
+                                         timestep=self.timestep, horizon=3.0, mode=mode, orientation=sp.orientation)
+            if self.debug:
+                print("Phantom agent of type {} with id {} added to scenario at position {}"
+                      .format(sp.agent_type, self.agent_manager.phantom_agents[-1].agent_id, sp.position))
+        self.agent_manager.update_real_agents(self.predictions)
+        if self.visualization is not None and self.plot:
+            self.visualization.draw_predictions(self.agent_manager.predictions, label=False)
+            self.visualization.show_plot(time=0.1)
+        return self.sensor_model.visible_area
+
+    def trajectory_safety_assessment(self, trajectory):
+        """interface.py:216-219."""
+        metrics, safety_assessment = self.metrics.evaluate_metrics(trajectory)
+        return metrics, safety_assessment
+
+    def assess_bundle(self, trajectories, want_pair=False, want_step=False):
+        """Whole sampled bundle at once: ``trajectories`` is [N, T, 5] (x, y, theta, v, a) as a tensor / array or a
+        sequence of trajectory objects.  Returns device tensors ``valid[N]``, ``summary[N, K]``, ``flags[N]``
+        (``engine.BundleResult``); every trajectory is valid when there are no phantom agents (metric.py:44-45)."""
+        return self.metrics.evaluate_bundle(trajectories, want_pair=want_pair, want_step=want_step)
+
+    def _update_time_step(self, timestep):
+        self.timestep = timestep
+        self.sensor_model.timestep = timestep
+        self.agent_manager.timestep = timestep
+
+    @staticmethod
+    def _load_config(filepath: str = None):
+        if isinstance(filepath, dict):          # extension: an already-parsed configuration
+            import copy
+            return copy.deepcopy(filepath)
+        if not filepath:
+            filepath = os.path.join(os.path.dirname(__file__), "config", "config.yaml")
+            print("Load default occlusion module settings!")
+        with open(filepath, "r") as file:
+            return yaml.safe_load(file)

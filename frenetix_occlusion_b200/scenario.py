@@ -100,9 +100,25 @@ def _points_in_polygon(P, poly):
     return (np.sum(cond & (x < xin), axis=1) % 2).astype(bool)
 
 
+class IntersectionIncomingElement:
+    def __init__(self, incoming_id, incoming_lanelets, successors_right, successors_straight, successors_left):
+        self.incoming_id = incoming_id
+        self.incoming_lanelets = set(incoming_lanelets)
+        self.successors_right = set(successors_right)
+        self.successors_straight = set(successors_straight)
+        self.successors_left = set(successors_left)
+
+
+class Intersection:
+    def __init__(self, intersection_id, incomings):
+        self.intersection_id = intersection_id
+        self.incomings = list(incomings)
+
+
 class LaneletNetwork:
-    def __init__(self, lanelets):
+    def __init__(self, lanelets, intersections=None):
         self.lanelets = list(lanelets)
+        self.intersections = list(intersections or [])
         self._by_id = {l.lanelet_id: l for l in self.lanelets}
 
     def find_lanelet_by_id(self, lanelet_id):
@@ -227,6 +243,14 @@ def load_commonroad_xml(path: str) -> Scenario:
         if ar is not None:
             l.adj_right, l.adj_right_same_direction = int(ar.attrib["ref"]), ar.attrib.get("drivingDir") == "same"
         lanelets.append(l)
+    intersections = []
+    for it in root.findall("intersection"):
+        incs = []
+        for inc in it.findall("incoming"):
+            refs = lambda tag: [int(n.attrib["ref"]) for n in inc.findall(tag)]  # noqa: E731
+            incs.append(IntersectionIncomingElement(int(inc.attrib["id"]), refs("incomingLanelet"), refs("successorsRight"),
+                                                    refs("successorsStraight"), refs("successorsLeft")))
+        intersections.append(Intersection(int(it.attrib["id"]), incs))
     obstacles = []
     for tag, role in (("staticObstacle", "static"), ("dynamicObstacle", "dynamic")):
         for ob in root.findall(tag):
@@ -242,4 +266,58 @@ def load_commonroad_xml(path: str) -> Scenario:
         goal = ppn.find("goalState/position/lanelet")
         pp = types.SimpleNamespace(planning_problem_id=int(ppn.attrib["id"]), initial_state=_state(ppn.find("initialState")),
                                    goal_lanelet=int(goal.attrib["ref"]) if goal is not None else None)
-    return Scenario(dt, LaneletNetwork(lanelets), obstacles, root.attrib.get("benchmarkID", ""), pp)
+    return Scenario(dt, LaneletNetwork(lanelets, intersections), obstacles, root.attrib.get("benchmarkID", ""), pp)
+
+
+# ------------------------------------------------------------------------------------------------
+def scenario_to_dict(sc: Scenario, ndigits: int = 6) -> dict:
+    """Compact JSON-able form of exactly what this path reads from a scenario (test fixtures)."""
+    r = lambda a: np.round(np.asarray(a, dtype=np.float64), ndigits).tolist()  # noqa: E731
+    ln = sc.lanelet_network
+    out = {"dt": sc.dt, "scenario_id": sc.scenario_id, "lanelets": [], "intersections": [], "obstacles": []}
+    for l in ln.lanelets:
+        out["lanelets"].append({"id": l.lanelet_id, "left": r(l.left_vertices), "right": r(l.right_vertices),
+                                "pred": l.predecessor, "succ": l.successor,
+                                "adj_left": [l.adj_left, l.adj_left_same_direction],
+                                "adj_right": [l.adj_right, l.adj_right_same_direction]})
+    for it in ln.intersections:
+        out["intersections"].append({"id": it.intersection_id, "incomings": [
+            {"id": e.incoming_id, "in": sorted(e.incoming_lanelets), "right": sorted(e.successors_right),
+             "straight": sorted(e.successors_straight), "left": sorted(e.successors_left)} for e in it.incomings]})
+    st = lambda s: [float(s.position[0]), float(s.position[1]), float(s.orientation), float(s.velocity), int(s.time_step)]  # noqa: E731
+    for o in sc.obstacles:
+        sh = o.obstacle_shape
+        out["obstacles"].append({"id": o.obstacle_id, "type": o.obstacle_type.value, "role": o.obstacle_role.value,
+                                 "shape": [sh.length, sh.width, float(sh.center[0]), float(sh.center[1]), sh.orientation],
+                                 "initial": r(st(o.initial_state)),
+                                 "states": None if o.prediction is None else r([st(s) for s in o.prediction.trajectory.state_list])})
+    pp = sc.planning_problem
+    if pp is not None:
+        out["planning_problem"] = {"id": pp.planning_problem_id, "initial": r(st(pp.initial_state)), "goal_lanelet": pp.goal_lanelet}
+    return out
+
+
+def scenario_from_dict(d: dict) -> Scenario:
+    def mk_state(v):
+        return State(position=np.array([v[0], v[1]]), orientation=float(v[2]), velocity=float(v[3]), acceleration=0.0,
+                     time_step=int(v[4]))
+    lanelets = []
+    for e in d["lanelets"]:
+        l = Lanelet(e["id"], e["left"], e["right"])
+        l.predecessor, l.successor = list(e["pred"]), list(e["succ"])
+        l.adj_left, l.adj_left_same_direction = e["adj_left"]
+        l.adj_right, l.adj_right_same_direction = e["adj_right"]
+        lanelets.append(l)
+    inters = [Intersection(it["id"], [IntersectionIncomingElement(e["id"], e["in"], e["right"], e["straight"], e["left"])
+                                      for e in it["incomings"]]) for it in d.get("intersections", [])]
+    obstacles = []
+    for o in d["obstacles"]:
+        sh = o["shape"]
+        shape = Rectangle(sh[0], sh[1], center=np.array([sh[2], sh[3]]), orientation=sh[4])
+        states = None if o["states"] is None else [mk_state(v) for v in o["states"]]
+        obstacles.append(Obstacle(o["id"], o["type"], o["role"], shape, mk_state(o["initial"]), states))
+    pp = None
+    if "planning_problem" in d:
+        p = d["planning_problem"]
+        pp = types.SimpleNamespace(planning_problem_id=p["id"], initial_state=mk_state(p["initial"]), goal_lanelet=p["goal_lanelet"])
+    return Scenario(d["dt"], LaneletNetwork(lanelets, inters), obstacles, d.get("scenario_id", ""), pp)

@@ -1,22 +1,45 @@
-"""Sensor model on the ray-cast visibility map (mirror of reference sensor_model.py:18-234).
+"""Sensor model (mirror of reference sensor_model.py:18-234) on the CUDA visibility kernels.
 
 Same constructor arguments and products (``visible_area``, ``occluded_area``, ``obstacle_occlusions``,
-``visible_objects_timestep``, per-obstacle ``current_visible`` / ``last_visible_at_ts``), but instead of
-shapely polygons the products are small objects over the polar first-hit map computed by
-``fo_visibility_raycast``."""
+``road_polygon``, ``visible_objects_timestep``, per-obstacle ``current_visible`` / ``last_visible_at_ts``).
+The reference materialises these as shapely polygons through one GEOS ``difference`` per road-border edge and
+obstacle; here they are *region objects* answering the predicates the spawn locator asks (``contains`` for
+sampled points) through ``fo_visibility_points``, plus the polar first-hit map of ``fo_visibility_raycast``
+(``VisibleArea.ranges`` / ``.exterior``) for the planner and the visible-obstacle list."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
 from . import _lib as L
-from .visibility import raycast_frames, ray_angle_params
+from .visibility import FrameGeometry, ray_angle_params
 
 
-class VisibleArea:
-    """Star-shaped visible region around the ego: ``range[r]`` along ``angle0 + r * dangle``."""
+class _Region:
+    """A planar region known through a point-membership predicate evaluated on the device."""
+    flag = 0
 
-    def __init__(self, ego_pos, angle0, dangle, ranges, hit, full_circle, sensor_radius):
+    def __init__(self, sensor_model):
+        self._sm = sensor_model
+
+    def contains(self, points):
+        """bool [M] for points [M,2] (a single point gives a python bool)."""
+        P = np.asarray(points, dtype=np.float64).reshape(-1, 2)
+        f, _, _ = self._sm._classify(P)
+        out = (f & self.flag) != 0
+        return out if out.size != 1 or np.ndim(points) > 1 else bool(out[0])
+
+    def intersects_points(self, points) -> bool:
+        return bool(np.any(np.atleast_1d(self.contains(points))))
+
+
+class VisibleArea(_Region):
+    """``SensorModel.visible_area``: star-shaped region around the ego.  ``ranges[r]`` is the first-hit distance
+    along ``angles[r]``; ``contains`` is exact (segment ego -> point against every opaque edge)."""
+    flag = L.PT_VISIBLE
+
+    def __init__(self, sensor_model, ego_pos, angle0, dangle, ranges, hit, full_circle, sensor_radius):
+        super().__init__(sensor_model)
         self.ego_pos = np.asarray(ego_pos, dtype=np.float64)
         self.angle0, self.dangle = float(angle0), float(dangle)
         self.ranges = np.asarray(ranges, dtype=np.float64)
@@ -28,28 +51,10 @@ class VisibleArea:
     def angles(self):
         return self.angle0 + self.dangle * np.arange(len(self.ranges))
 
-    def ray_index(self, points):
-        """Fractional ray index of the direction ego -> point, and whether it lies inside the fan."""
-        d = np.asarray(points, dtype=np.float64).reshape(-1, 2) - self.ego_pos
-        rel = np.arctan2(d[:, 1], d[:, 0]) - self.angle0
-        rel = np.mod(rel, 2.0 * np.pi)
-        idx = rel / self.dangle
-        n = len(self.ranges)
-        inside = np.ones(len(d), dtype=bool) if self.full_circle else idx <= n - 1
-        return idx, inside, np.hypot(d[:, 0], d[:, 1])
-
-    def contains(self, points, margin=0.0):
-        """Point(s) visible: inside the fan and closer than the first hit of both neighbouring rays."""
-        idx, inside, dist = self.ray_index(points)
-        n = len(self.ranges)
-        i0 = np.floor(idx).astype(int) % n
-        i1 = (i0 + 1) % n if self.full_circle else np.minimum(i0 + 1, n - 1)
-        rng = np.minimum(self.ranges[i0], self.ranges[i1])
-        out = inside & (dist <= rng + margin)
-        return out if out.size > 1 else bool(out[0])
-
     @property
     def exterior(self):
+        """Polar fan polygon (what the reference returns to the planner as a shapely polygon, clipped to the
+        road there; here the un-clipped star polygon)."""
         a = self.angles
         ring = self.ego_pos + np.stack((self.ranges * np.cos(a), self.ranges * np.sin(a)), -1)
         if not self.full_circle:
@@ -58,54 +63,41 @@ class VisibleArea:
 
     @property
     def area(self):
-        return float(0.5 * np.sum(self.ranges[:-1] * self.ranges[1:] * np.sin(self.dangle))
-                     + (0.5 * self.ranges[-1] * self.ranges[0] * np.sin(self.dangle) if self.full_circle else 0.0))
+        s = np.sin(self.dangle)
+        a = 0.5 * np.sum(self.ranges[:-1] * self.ranges[1:]) * s
+        if self.full_circle:
+            a += 0.5 * self.ranges[-1] * self.ranges[0] * s
+        return float(a)
 
     @property
     def is_empty(self):
         return not bool(np.any(self.ranges > 0))
 
 
-class OccludedArea:
-    """(+-90 deg sector of radius 1.5 R) ∩ road - visible area (sensor_model.py:85-93) as a predicate."""
+class OccludedArea(_Region):
+    """(+-90 deg sector of radius 1.5 R) ∩ road − visible area (sensor_model.py:85-93)."""
+    flag = L.PT_OCCLUDED
 
-    def __init__(self, visible_area, ego_orientation, lanelet_network, factor=1.5):
-        self.visible_area = visible_area
-        self.ego_orientation = float(ego_orientation)
-        self.lanelet_network = lanelet_network
-        self.radius = factor * visible_area.sensor_radius
+
+class RoadArea(_Region):
+    """Union of all lanelet polygons (sensor_model.py:195-199)."""
+    flag = L.PT_ON_ROAD
+
+
+class ObstacleShadow(_Region):
+    """``obstacle_occlusions[id]`` = shadow of one obstacle minus the obstacle itself (sensor_model.py:182-183)."""
+    flag = L.PT_FOCUS_SHADOW
+
+    def __init__(self, sensor_model, index, ray_ids):
+        super().__init__(sensor_model)
+        self.index = int(index)
+        self.ray_ids = np.asarray(ray_ids, dtype=int)
 
     def contains(self, points):
         P = np.asarray(points, dtype=np.float64).reshape(-1, 2)
-        d = P - self.visible_area.ego_pos
-        rel = np.mod(np.arctan2(d[:, 1], d[:, 0]) - self.ego_orientation + np.pi, 2 * np.pi) - np.pi
-        out = (np.abs(rel) <= np.pi / 2) & (np.hypot(d[:, 0], d[:, 1]) <= self.radius)
-        out &= self.lanelet_network.points_on_road(P)
-        out &= ~np.atleast_1d(self.visible_area.contains(P))
-        return out if out.size > 1 else bool(out[0])
-
-
-class ObstacleShadow:
-    """Shadow of one obstacle (``obstacle_occlusions[id]``, sensor_model.py:182-183): the fan of rays whose
-    first hit is this obstacle, from the hit outwards."""
-
-    def __init__(self, visible_area, ray_ids):
-        self.visible_area = visible_area
-        self.ray_ids = np.asarray(ray_ids, dtype=int)
-
-    @property
-    def angular_interval(self):
-        a = self.visible_area.angles[self.ray_ids]
-        return float(a.min()), float(a.max())
-
-    def contains(self, points):
-        idx, inside, dist = self.visible_area.ray_index(points)
-        n = len(self.visible_area.ranges)
-        i0 = np.round(idx).astype(int) % n
-        mask = np.zeros(n, dtype=bool)
-        mask[self.ray_ids] = True
-        out = inside & mask[i0] & (dist > self.visible_area.ranges[i0]) & (dist <= self.visible_area.ranges[i0] + 100.0)
-        return out if out.size > 1 else bool(out[0])
+        f, _, _ = self._sm._classify(P, focus=self.index)
+        out = (f & self.flag) != 0
+        return out if out.size != 1 or np.ndim(points) > 1 else bool(out[0])
 
 
 class SensorModel:
@@ -128,49 +120,99 @@ class SensorModel:
         self.obstacle_occlusions = {}
         self.all_obstacle_occlusions_polygon = None
         self.visible_objects_timestep = []
-        # road border = exterior of the union of all lanelet polygons (sensor_model.py:195-199)
-        self.road_polygon = lanelet_network
+        # road polygon = union of all lanelet polygons; its exterior is what casts the border shadows
+        # (sensor_model.py:131-155, 195-199)
+        self.lanelet_polygons = [np.asarray(p, dtype=np.float64) for p in _lanelet_polygons(lanelet_network)]
         self.road_border = lanelet_network.road_border_segments() if hasattr(lanelet_network, "road_border_segments") \
-            else np.zeros((0, 4))
+            else _border_from_polygons(self.lanelet_polygons)
+        self.road_polygon = RoadArea(self)
+        self._frame = None
+        self._obstacle_index = {}
 
+    # ---- device calls (the only places this class touches the C ABI) -----------------------------------
+    def _build_frame(self, rect, flags, border):
+        return FrameGeometry(self.ego_pos, self.ego_orientation, rect, flags, border, self.lanelet_polygons,
+                             self.sensor_radius, self.sensor_angle, device=self.device)
+
+    def _raycast(self):
+        res = self._frame.raycast(self.n_rays)
+        torch.cuda.current_stream(torch.device(self.device)).synchronize()
+        O = self._frame.n_obstacles
+        return res.range[0].cpu().numpy(), res.hit[0].cpu().numpy(), \
+            (res.visible[0].cpu().numpy() if O else np.zeros(0, np.uint8))
+
+    def _classify(self, points, focus=-1):
+        if self._frame is None:
+            raise RuntimeError("calc_visible_and_occluded_area has not been called yet")
+        return self._frame.classify(points, focus_obstacle=focus)
+
+    # ---- sensor_model.py:41-101 ----------------------------------------------------------------------------
     def calc_visible_and_occluded_area(self, timestep, ego_pos, ego_orientation, obstacles):
-        """sensor_model.py:41-101 on the polar map: one launch of the ray-cast kernel for this frame."""
         self.ego_pos = np.asarray(ego_pos, dtype=np.float64)
         self.ego_orientation = float(ego_orientation)
         self.visible_objects_timestep = []
         self.obstacle_occlusions.clear()
         obs = [o for o in obstacles if o.current_pos is not None]
         O = len(obs)
-        rect = np.zeros((1, max(O, 1), 5))
-        flags = np.zeros((1, max(O, 1)), dtype=np.uint8)
+        rect = np.zeros((O, 5))
+        flags = np.zeros(O, dtype=np.uint8)
         for k, o in enumerate(obs):
-            rect[0, k] = o.as_rect()
-            flags[0, k] = L.RECT_EXISTS | (L.RECT_TRANSPARENT if o.cr_obstacle.obstacle_type.value == "bicycle" else 0)
-        # everything relative to the ego position (float64 shift before the float32 cast)
-        rect[0, :, 0] -= self.ego_pos[0]
-        rect[0, :, 1] -= self.ego_pos[1]
-        border = self.road_border - np.tile(self.ego_pos, 2) if len(self.road_border) else None
-        if border is not None:      # only segments that can matter for this frame
-            near = np.minimum(np.hypot(border[:, 0], border[:, 1]), np.hypot(border[:, 2], border[:, 3])) \
-                <= self.sensor_radius + 5.0
+            rect[k] = o.as_rect()
+            flags[k] = L.RECT_EXISTS | (L.RECT_TRANSPARENT if o.cr_obstacle.obstacle_type.value == "bicycle" else 0)
+        border = self.road_border
+        if len(border):     # only segments that can matter for this frame (occluded area reaches 1.5 R)
+            rel = border - np.tile(self.ego_pos, 2)
+            near = _segment_distance_to_origin(rel) <= 1.5 * self.sensor_radius + 1.0
             border = border[near]
-        ego = np.array([[0.0, 0.0, self.ego_orientation]])
-        res = raycast_frames(ego, rect[:, :O], flags[:, :O], border, self.sensor_radius, self.sensor_angle, self.n_rays,
-                             device=self.device)
-        torch.cuda.current_stream(torch.device(self.device)).synchronize()
-        rng = res.range[0].cpu().numpy()
-        hit = res.hit[0].cpu().numpy()
-        vis = res.visible[0].cpu().numpy() if O else np.zeros(0, np.uint8)
+        self._frame = self._build_frame(rect, flags, border)
+        self._obstacle_index = {o.cr_obstacle.obstacle_id: k for k, o in enumerate(obs)}
+        rng, hit, vis = self._raycast()
         a0, da = ray_angle_params(self.ego_orientation, self.sensor_angle, self.n_rays)
-        self.visible_area = VisibleArea(self.ego_pos, float(a0), float(da), rng, hit, self.sensor_angle >= 359.9,
+        self.visible_area = VisibleArea(self, self.ego_pos, float(a0), float(da), rng, hit, self.sensor_angle >= 359.9,
                                         self.sensor_radius)
+        # visible obstacles: the reference intersects each obstacle polygon with the (road-clipped) visible area
+        # buffered by 1 cm (sensor_model.py:59-76); here: some ray ends on the obstacle at a point of the road
+        ang = self.visible_area.angles
         for k, o in enumerate(obs):
-            if vis[k]:                                                   # sensor_model.py:68-76
+            rays = np.nonzero(hit == k)[0]
+            seen = bool(vis[k])
+            if seen and len(rays):
+                pts = self.ego_pos + (rng[rays] - 1e-3)[:, None] * np.stack((np.cos(ang[rays]), np.sin(ang[rays])), -1)
+                f, _, _ = self._classify(pts)
+                seen = bool(np.any(f & L.PT_ON_ROAD))
+            if seen:
                 self.visible_objects_timestep.append(o.cr_obstacle.obstacle_id)
                 o.current_visible = True
                 o.last_visible_at_ts = timestep
-            rays = np.nonzero(hit == k)[0]
             if len(rays):                                                # sensor_model.py:180-183
-                self.obstacle_occlusions[o.cr_obstacle.obstacle_id] = ObstacleShadow(self.visible_area, rays)
-        self.occluded_area = OccludedArea(self.visible_area, self.ego_orientation, self.lanelet_network)
+                self.obstacle_occlusions[o.cr_obstacle.obstacle_id] = ObstacleShadow(self, k, rays)
+        self.occluded_area = OccludedArea(self)
         return self.visible_area
+
+
+def _lanelet_polygons(lanelet_network):
+    if hasattr(lanelet_network, "lanelet_polygons") and not callable(getattr(lanelet_network, "lanelet_polygons")):
+        polys = lanelet_network.lanelet_polygons
+        if polys and hasattr(polys[0], "vertices"):           # commonroad-io Polygon objects
+            return [np.asarray(p.vertices)[:-1] if np.allclose(p.vertices[0], p.vertices[-1]) else np.asarray(p.vertices)
+                    for p in polys]
+        return polys
+    return [np.concatenate((l.left_vertices, l.right_vertices[::-1])) for l in lanelet_network.lanelets]
+
+
+def _segment_distance_to_origin(seg):
+    a, b = seg[:, :2], seg[:, 2:]
+    e = b - a
+    l2 = np.maximum((e ** 2).sum(1), 1e-18)
+    t = np.clip(-(a * e).sum(1) / l2, 0.0, 1.0)
+    p = a + t[:, None] * e
+    return np.hypot(p[:, 0], p[:, 1])
+
+
+def _border_from_polygons(polys):
+    from .scenario import LaneletNetwork, Lanelet
+    lanelets = []
+    for i, p in enumerate(polys):
+        h = len(p) // 2
+        lanelets.append(Lanelet(i, p[:h], p[h:][::-1]))
+    return LaneletNetwork(lanelets).road_border_segments()

@@ -80,3 +80,73 @@ def raycast_frames(ego, rect, rect_flags, boundary, sensor_radius: float, sensor
         a0, da = ray_angle_params(np.asarray(ego, dtype=np.float64).reshape(-1, 3)[:, 2], sensor_angle_deg, n_rays)
         out.angles0, out.dangle = a0, da
     return out
+
+
+class FrameGeometry:
+    """One sensor frame resident on the device: ego pose, obstacle rectangles, opaque road-border segments and
+    the lanelet polygons -- everything ``fo_visibility_raycast`` and ``fo_visibility_points`` read.  All
+    coordinates are relative to ``origin`` (subtracted in float64 before the float32 cast)."""
+
+    def __init__(self, origin, heading, rect, rect_flags, boundary, polygons, sensor_radius, sensor_angle_deg,
+                 occluded_factor=1.5, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("frenetix_occlusion_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.origin = np.asarray(origin, dtype=np.float64).reshape(2)
+        self.heading = float(heading)
+        self.sensor_radius, self.sensor_angle_deg = float(sensor_radius), float(sensor_angle_deg)
+        self.occluded_radius = float(occluded_factor) * float(sensor_radius)
+        rect = np.array(rect, dtype=np.float64).reshape(-1, 5)
+        rect[:, 0] -= self.origin[0]
+        rect[:, 1] -= self.origin[1]
+        self.n_obstacles = len(rect)
+        bnd = np.zeros((0, 4)) if boundary is None else np.asarray(boundary, dtype=np.float64).reshape(-1, 4)
+        bnd = bnd - np.tile(self.origin, 2)
+        self.n_boundary = len(bnd)
+        polys = [np.asarray(p, dtype=np.float64).reshape(-1, 2) - self.origin for p in (polygons or [])]
+        self.n_polygons = len(polys)
+        off = np.concatenate(([0], np.cumsum([len(p) for p in polys]))).astype(np.int32)
+        xy = np.concatenate(polys) if polys else np.zeros((0, 2))
+        self.host = {"ego": np.array([0.0, 0.0, self.heading]), "rect": rect, "flags": np.asarray(rect_flags, np.uint8).reshape(-1),
+                     "boundary": bnd, "polygons": polys}
+        with torch.cuda.device(self.device):
+            self.ego_d = torch.tensor([[0.0, 0.0, self.heading]], dtype=torch.float32, device=self.device)
+            self.rect_d = torch.from_numpy(rect.astype(np.float32)).to(self.device)
+            self.flags_d = torch.from_numpy(self.host["flags"].copy()).to(self.device)
+            self.bnd_d = torch.from_numpy(bnd.astype(np.float32)).to(self.device)
+            self.poly_xy_d = torch.from_numpy(xy.astype(np.float32)).to(self.device)
+            self.poly_off_d = torch.from_numpy(off).to(self.device)
+
+    def raycast(self, n_rays: int) -> VisibilityResult:
+        O = self.n_obstacles
+        return raycast_frames(self.ego_d, self.rect_d.reshape(1, O, 5), self.flags_d.reshape(1, O),
+                              self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg,
+                              n_rays, device=self.device)
+
+    def classify(self, points, focus_obstacle: int = -1):
+        """Classify world-frame points [M,2]: returns host arrays (flags uint32, blocker int32, lanelets uint64)."""
+        P = np.asarray(points, dtype=np.float64).reshape(-1, 2) - self.origin
+        M = len(P)
+        if M == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.int32), np.zeros(0, np.uint64)
+        dev = self.device
+        with torch.cuda.device(dev):
+            pts = torch.from_numpy(P.astype(np.float32)).to(dev)
+            flags = torch.empty(M, dtype=torch.int32, device=dev)
+            blocker = torch.empty(M, dtype=torch.int32, device=dev)
+            lan = torch.empty(M, dtype=torch.int64, device=dev)
+            a = L.FoPointQueryArgs()
+            a.n_points, a.n_obstacles, a.n_boundary, a.n_polygons = M, self.n_obstacles, self.n_boundary, self.n_polygons
+            a.ego, a.points = self.ego_d.data_ptr(), pts.data_ptr()
+            a.rect = self.rect_d.data_ptr() if self.n_obstacles else None
+            a.rect_flags = self.flags_d.data_ptr() if self.n_obstacles else None
+            a.boundary = self.bnd_d.data_ptr() if self.n_boundary else None
+            a.poly_xy = self.poly_xy_d.data_ptr() if self.n_polygons else None
+            a.poly_off = self.poly_off_d.data_ptr() if self.n_polygons else None
+            a.sensor_radius, a.sensor_angle_deg = self.sensor_radius, self.sensor_angle_deg
+            a.occluded_radius, a.focus_obstacle = self.occluded_radius, int(focus_obstacle)
+            a.flags, a.blocker, a.lanelets = flags.data_ptr(), blocker.data_ptr(), lan.data_ptr()
+            L.check(L.lib.fo_visibility_points(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                    "fo_visibility_points")
+            out = (flags.cpu().numpy().view(np.uint32), blocker.cpu().numpy(), lan.cpu().numpy().view(np.uint64))
+        return out

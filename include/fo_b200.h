@@ -184,6 +184,47 @@ typedef struct FoVisibilityArgs {
 
 int fo_visibility_raycast(const FoVisibilityArgs *args, void *stream);
 
+/* ---- stage 1 -> spawn locator: exact visibility / occlusion / road membership of query points -----
+ * Replaces the shapely predicates SpawnLocator evaluates against SensorModel's products
+ * (spawn_locator.py:263-275, 298, 406-444, 521, 552): `within` / `intersects` of points, lines and discs
+ * with visible_area (sensor_model.py:79), occluded_area (sensor_model.py:85-93), road_polygon
+ * (sensor_model.py:195-199) and obstacle_occlusions[id] (sensor_model.py:182-183).  The host samples the
+ * geometry it is interested in (lines, disc rims, raster windows) and this kernel classifies every sample
+ * with the reference's own construction evaluated point-wise: a point is shadowed iff the segment
+ * ego -> point crosses an opaque edge (border edge of road ∩ sector, sensor_model.py:137-155; non-bicycle
+ * obstacle, sensor_model.py:174-191) or lies inside an opaque obstacle.  One frame per call. */
+enum {
+  FO_PT_IN_SENSOR = 1u << 0,    /* inside the sensor sector: radius and field of view (sensor_model.py:114-125) */
+  FO_PT_ON_ROAD = 1u << 1,      /* inside at least one lanelet polygon (road_polygon) */
+  FO_PT_SHADOWED = 1u << 2,     /* segment ego -> point crosses an opaque edge */
+  FO_PT_IN_OBSTACLE = 1u << 3,  /* inside an existing, opaque obstacle rectangle */
+  FO_PT_VISIBLE = 1u << 4,      /* IN_SENSOR & ON_ROAD & !SHADOWED & !IN_OBSTACLE  == within visible_area */
+  FO_PT_OCCLUDED = 1u << 5,     /* ON_ROAD & within +-90 deg of the heading & closer than occluded_radius
+                                   & !VISIBLE                                       == within occluded_area */
+  FO_PT_FOCUS_SHADOW = 1u << 6  /* behind (not inside) obstacle `focus_obstacle` as seen from the ego
+                                                                  == within obstacle_occlusions[id] */
+};
+
+typedef struct FoPointQueryArgs {
+  int32_t n_points, n_obstacles, n_boundary, n_polygons;
+  const float *ego;            /* dev [3] (x, y, heading) */
+  const float *points;         /* dev [M, 2] query points, same frame as ego / rect / boundary */
+  const float *rect;           /* dev [O, 5] as FoVisibilityArgs.rect (one frame) */
+  const uint8_t *rect_flags;   /* dev [O] FO_RECT_* */
+  const float *boundary;       /* dev [B, 4] opaque road-border segments */
+  const float *poly_xy;        /* dev [V, 2] lanelet polygon rings (lanelet.polygon), concatenated, open rings */
+  const int32_t *poly_off;     /* dev [n_polygons + 1] offsets into poly_xy */
+  float sensor_radius, sensor_angle_deg;
+  float occluded_radius;       /* 1.5 * sensor_radius (sensor_model.py:88) */
+  int32_t focus_obstacle;      /* obstacle index for FO_PT_FOCUS_SHADOW, or -1 */
+  uint32_t *flags;             /* dev [M] FO_PT_* */
+  int32_t *blocker;            /* dev [M] first opaque thing the segment ego -> point meets: obstacle index |
+                                  FO_HIT_BOUNDARY | FO_HIT_NONE; may be NULL */
+  uint64_t *lanelets;          /* dev [M] bit i set = point inside polygon i (i < 64); may be NULL */
+} FoPointQueryArgs;
+
+int fo_visibility_points(const FoPointQueryArgs *args, void *stream);
+
 /* ---- stage 2: phantom-agent rollouts ---------------------------------------------------------------
  * Constant-velocity pedestrian prediction: OAPPedestrianAgent._create_ped_trajectory (agent.py:451-505)
  * + _create_cr_predictions (agent.py:520-536) + create_cov_matrix (agent.py:260-280), written straight

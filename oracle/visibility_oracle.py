@@ -246,3 +246,73 @@ def rollout_path(path, x0, y0, v0, dt, horizon, t1=3.0, var0=0.1, var_factor=1.0
     return {"x": pts[j, 0] + u * seg[j, 0] - d * ty, "y": pts[j, 1] + u * seg[j, 1] + d * tx,
             "yaw": np.arctan2(ty, tx) + np.arctan2(dd, vl), "v": v, "var": var0 * np.power(var_factor, k),
             "sample": best_k, "s0": s0, "d0": d0}
+
+
+# ------------------------------------------------------------------------------------------------
+PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW = 1, 2, 4, 8, 16, 32, 64
+
+
+def points_in_polygon(P, poly):
+    """Even-odd rule in float64 for points [M,2] against one open ring [V,2]."""
+    P = np.asarray(P, dtype=np.float64).reshape(-1, 2)
+    poly = np.asarray(poly, dtype=np.float64).reshape(-1, 2)
+    x, y = P[:, 0][:, None], P[:, 1][:, None]
+    x1, y1 = poly[:, 0][None], poly[:, 1][None]
+    x0, y0 = np.roll(poly[:, 0], 1)[None], np.roll(poly[:, 1], 1)[None]
+    cond = (y0 > y) != (y1 > y)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xin = (x1 - x0) * (y - y0) / (y1 - y0) + x0
+    return (np.sum(cond & (x < xin), axis=1) % 2).astype(bool)
+
+
+def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_deg, occluded_radius, focus=-1):
+    """Point-wise evaluation of the reference's visible / occluded area construction (float64):
+    visible_area = road ∩ sector − border-edge shadow quads − obstacles − obstacle shadows
+    (sensor_model.py:103-193), occluded_area = (±90° sector of radius 1.5 R) ∩ road − visible_area
+    (sensor_model.py:85-93), obstacle_occlusions[id] = shadow(id) − obstacle(id) (sensor_model.py:182-183).
+    Returns (flags uint32 [M], lanelet bit mask uint64 [M])."""
+    P = np.asarray(P, dtype=np.float64).reshape(-1, 2)
+    ego = np.asarray(ego, dtype=np.float64)
+    e = ego[:2]
+    d = P - e
+    r = np.hypot(d[:, 0], d[:, 1])
+    rel = (np.arctan2(d[:, 1], d[:, 0]) - ego[2] + np.pi) % (2 * np.pi) - np.pi
+    in_sensor = r <= sensor_radius
+    if fov_deg < 359.9:
+        in_sensor &= np.abs(rel) <= np.radians(fov_deg) / 2
+    shadow = np.zeros(len(P), dtype=bool)
+    if boundary is not None:
+        for b in np.asarray(boundary, dtype=np.float64).reshape(-1, 4):
+            v1, v2 = b[:2], b[2:]
+            if np.allclose(v1, v2):
+                continue
+            shadow |= _in_convex_quad(P, [v1, v2, v2 + 100 * (v2 - e), v1 + 100 * (v1 - e)])
+    rect = np.asarray(rect, dtype=np.float64).reshape(-1, 5)
+    flags = np.asarray(flags).reshape(-1)
+    cor = rect_corners(rect)
+    in_obst = np.zeros(len(P), dtype=bool)
+    focus_shadow = np.zeros(len(P), dtype=bool)
+    for o in range(len(rect)):
+        if not (flags[o] & RECT_EXISTS) or (flags[o] & RECT_TRANSPARENT):
+            continue
+        c1, c2 = identify_projection_points(e, cor[o])
+        u1 = (c1 - e) / np.linalg.norm(c1 - e)
+        u2 = (c2 - e) / np.linalg.norm(c2 - e)
+        wedge = _in_convex_quad(P, [c1, c2, c2 + u2 * 100, c1 + u1 * 100])
+        inside = _in_convex_quad(P, cor[o])
+        shadow |= wedge & ~inside
+        in_obst |= inside
+        if o == focus:
+            focus_shadow = wedge & ~inside
+    lan = np.zeros(len(P), dtype=np.uint64)
+    on_road = np.zeros(len(P), dtype=bool)
+    for i, poly in enumerate(polygons):
+        m = points_in_polygon(P, poly)
+        on_road |= m
+        if i < 64:
+            lan |= np.where(m, np.uint64(1) << np.uint64(i), np.uint64(0))
+    visible = in_sensor & on_road & ~shadow & ~in_obst
+    occluded = on_road & ~visible & (np.abs(rel) <= np.pi / 2) & (r <= occluded_radius)
+    f = (in_sensor * PT_IN_SENSOR + on_road * PT_ON_ROAD + shadow * PT_SHADOWED + in_obst * PT_IN_OBSTACLE
+         + visible * PT_VISIBLE + occluded * PT_OCCLUDED + focus_shadow * PT_FOCUS_SHADOW).astype(np.uint32)
+    return f, lan
