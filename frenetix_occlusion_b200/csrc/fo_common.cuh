@@ -35,22 +35,33 @@ struct __align__(16) AgentParams {
   float pad;       // circumradius sqrt(hl^2 + hw^2)
 };
 
+// followed by a TIME-MAJOR copy for the sweep kernel (lane = agent, consecutive lanes read consecutive
+// entries): [ float4 t0[Tp*Ap] | float tv[Tp*Ap] ], Ap = A rounded up to 32, padding entries zeroed;
+//   t0[i*Ap + a] = s0[a*Tp + i],  tv[i*Ap + a] = v_i of agent a
 struct AgentTableView {
   const float4* s0;
   const float4* s1;
   const float2* s2;
   const AgentParams* prm;
+  const float4* t0;
+  const float* tv;
+  int Ap;
 };
 
+__host__ __device__ inline int agent_pad(int A) { return (A + 31) & ~31; }
 __host__ __device__ inline size_t agent_table_bytes(int A, int Tp) {
-  return (size_t)A * Tp * (2 * sizeof(float4) + sizeof(float2)) + (size_t)A * sizeof(AgentParams);
+  return (size_t)A * Tp * (2 * sizeof(float4) + sizeof(float2)) + (size_t)A * sizeof(AgentParams) +
+         (size_t)agent_pad(A) * Tp * (sizeof(float4) + sizeof(float));
 }
 __host__ __device__ inline AgentTableView agent_table_view(const void* base, int A, int Tp) {
   AgentTableView v;
   v.s0 = reinterpret_cast<const float4*>(base);
   v.s1 = v.s0 + (size_t)A * Tp;
   v.prm = reinterpret_cast<const AgentParams*>(v.s1 + (size_t)A * Tp);
-  v.s2 = reinterpret_cast<const float2*>(v.prm + A);
+  v.t0 = reinterpret_cast<const float4*>(v.prm + A);
+  v.Ap = agent_pad(A);
+  v.tv = reinterpret_cast<const float*>(v.t0 + (size_t)v.Ap * Tp);
+  v.s2 = reinterpret_cast<const float2*>(v.tv + (size_t)v.Ap * Tp);
   return v;
 }
 

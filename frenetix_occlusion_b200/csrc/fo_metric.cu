@@ -1,4 +1,6 @@
 // Host entry points of the dense metric core: agent-table packing and kernel dispatch.
+#include <stdlib.h>
+
 #include "fo_metric_dev.cuh"
 
 namespace fo {
@@ -25,9 +27,15 @@ __device__ __forceinline__ int protection_model(int kind) {  // harm_model.py:15
   }
 }
 
-__global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, float4* s1, float2* s2, AgentParams* prm) {
+__global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, float4* s1, float2* s2, AgentParams* prm,
+                                      float4* t0, float* tv, int Ap) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int A = raw.n_agents, Tp = raw.t_stride;
+  if (idx >= A * Tp && idx < Ap * Tp) {      // padding agents of the time-major copy
+    const int a = idx / Tp, i = idx - a * Tp;
+    t0[(size_t)i * Ap + a] = make_float4(0, 0, 1, 0);
+    tv[(size_t)i * Ap + a] = 0.0f;
+  }
   if (idx < A * Tp) {
     const int a = idx / Tp, i = idx - a * Tp;
     float4 o0 = make_float4(0, 0, 1, 0), o1 = make_float4(0, 0, 0, 0);
@@ -46,6 +54,8 @@ __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, 
     s0[idx] = o0;
     s1[idx] = o1;
     s2[idx] = o2;
+    t0[(size_t)i * Ap + a] = o0;
+    tv[(size_t)i * Ap + a] = o1.y;
   }
   if (idx < A) {
     AgentParams p;
@@ -87,18 +97,28 @@ extern "C" int fo_agents_pack(const FoAgentsRaw* raw, const FoVehicle* vehicle, 
     return FO_ERR_INVALID_ARG;
   }
   fo::AgentTableView v = fo::agent_table_view(table_dev, A, Tp);
-  const int total = A * Tp;
+  const int total = v.Ap * Tp;
   fo::fo_agents_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       *raw, vehicle->mass, const_cast<float4*>(v.s0), const_cast<float4*>(v.s1), const_cast<float2*>(v.s2),
-      const_cast<fo::AgentParams*>(v.prm));
+      const_cast<fo::AgentParams*>(v.prm), const_cast<float4*>(v.t0), const_cast<float*>(v.tv), v.Ap);
   fo::count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;
 }
 
 static int g_num_sms = 0;
+static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, void* stream);
 
-extern "C" int fo_metric_bundle(const FoMetricArgs* a, void* stream) {
+extern "C" int fo_metric_bundle(const FoMetricArgs* a, void* stream) { return metric_bundle_impl(a, nullptr, stream); }
+
+extern "C" int fo_metric_stats(const FoMetricArgs* a, uint64_t* counters_dev, void* stream) {
+  if (!counters_dev) { fo::set_error("fo_metric_stats: counters_dev must not be NULL"); return FO_ERR_INVALID_ARG; }
+  if (a && (a->pair || a->step)) { fo::set_error("fo_metric_stats: summary outputs only"); return FO_ERR_INVALID_ARG; }
+  FO_CUDA_TRY(cudaMemsetAsync(counters_dev, 0, FO_STATS_K * sizeof(uint64_t), (cudaStream_t)stream));
+  return metric_bundle_impl(a, reinterpret_cast<unsigned long long*>(counters_dev), stream);
+}
+
+static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, void* stream) {
   if (!a) { fo::set_error("fo_metric_bundle: NULL args"); return FO_ERR_INVALID_ARG; }
   if (a->n_traj < 0 || a->n_states < 0 || a->n_agents < 0) { fo::set_error("fo_metric_bundle: negative size"); return FO_ERR_INVALID_ARG; }
   if (a->n_traj == 0) return FO_OK;
@@ -131,8 +151,16 @@ extern "C" int fo_metric_bundle(const FoMetricArgs* a, void* stream) {
   k.thr_harm = a->thr_harm; k.thr_risk = a->thr_risk; k.thr_be = a->thr_be; k.thr_cp = a->thr_cp;
   k.thr_ttc = a->thr_ttc; k.thr_dce = a->thr_dce;
   k.valid = a->valid; k.summary = a->summary; k.flags = a->flags; k.pair = a->pair; k.step = a->step;
+  k.stats = stats;
 
   cudaStream_t st = (cudaStream_t)stream;
   if (k.pair || k.step) return fo::launch_metric_detail(k, g_num_sms, st);
+  // summary path: lane = agent sweep when a 32-agent lane tile is reasonably full, else the flattened
+  // (agent x step) mapping that keeps every lane busy for a handful of agents (the planner's usual case)
+  static const bool force_flat = getenv("FO_FORCE_FLAT") != nullptr;     // measurement switches
+  static const bool force_sweep = getenv("FO_FORCE_SWEEP") != nullptr;
+  const int lanes_used = k.A % 32 == 0 ? 32 : k.A % 32;
+  const bool sweep_ok = k.A >= 24 && (k.A >= 96 || lanes_used >= 24);
+  if (((sweep_ok || force_sweep) && !force_flat) || stats) return fo::launch_metric_sweep(k, g_num_sms, st);
   return fo::launch_metric_flat(k, g_num_sms, st);
 }

@@ -28,6 +28,7 @@ struct MetricKArgs {
   uint32_t* flags;
   float* pair;
   float* step;
+  unsigned long long* stats;   // optional [8] work counters (see fo_metric_stats), NULL in production launches
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -84,6 +85,53 @@ __device__ __forceinline__ float half_derf(float a, float b) {
   return 0.5f * r;
 }
 
+// erfc(z), z >= 0, fractional error < 1.2e-7 in exact arithmetic (Chebyshev fit of Numerical Recipes' erfcc:
+// t = 1/(1 + z/2), erfc = t exp(-z^2 + P9(t))); about 4e-6 relative in float32 because of the exponent's
+// magnitude -- two orders below the 1e-4 parity tolerance.  18 instructions instead of erfcf's ~45.
+__device__ __forceinline__ float erfc_pos_fast(float z) {
+  const float t = __fdividef(1.0f, fmaf(0.5f, z, 1.0f));
+  float p = 0.17087277f;
+  p = fmaf(p, t, -0.82215223f);
+  p = fmaf(p, t, 1.48851587f);
+  p = fmaf(p, t, -1.13520398f);
+  p = fmaf(p, t, 0.27886807f);
+  p = fmaf(p, t, -0.18628806f);
+  p = fmaf(p, t, 0.09678418f);
+  p = fmaf(p, t, 0.37409196f);
+  p = fmaf(p, t, 1.00002368f);
+  p = fmaf(p, t, -1.26551223f);
+  return t * __expf(fmaf(-z, z, p));
+}
+
+// Collision probability of one gated step (collision_probability.py:94-122): Gaussian mass of the 3 obstacle
+// points over the 3 axis-aligned ego boxes, divided by 3.  (mx, my) = obstacle position i-1 minus ego position i,
+// (hx, hy) = half buffered length along yaw_i, (bx, by) = (L/3)(cos, sin theta_i), s2 = 1/(sqrt2 sigma_{x,y}).
+// A factor whose standardised interval lies beyond 4.7 (erfc < 3e-11) contributes less than the 1e-10 that the
+// comparison floor of 2e-7 can resolve and is skipped before any erfc is evaluated.
+__device__ __forceinline__ float cp_gauss_boxes(float mx, float my, float hx, float hy, float bx, float by, float2 s2,
+                                                float L6, float W2) {
+  constexpr float kFar = 4.7f;
+  float prob = 0.0f;
+#pragma unroll 1
+  for (int mb = 0; mb < 9; ++mb) {
+    const int m = mb / 3, bb = mb - 3 * m;
+    const float fm = (m == 0) ? 0.0f : (m == 1 ? 1.0f : -1.0f);
+    const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
+    const float uy = fmaf(fm, hy, my), cyb = fb * by;
+    const float ya = (cyb - W2 - uy) * s2.y, yb = (cyb + W2 - uy) * s2.y;     // ya < yb
+    if (ya > kFar || yb < -kFar) continue;
+    const float ux = fmaf(fm, hx, mx), cxb = fb * bx;
+    const float xa = (cxb - L6 - ux) * s2.x, xb = (cxb + L6 - ux) * s2.x;
+    if (xa > kFar || xb < -kFar) continue;
+    const float eya = erfc_pos_fast(fabsf(ya)), eyb = erfc_pos_fast(fabsf(yb));
+    const float py = ((ya > 0.0f) == (yb > 0.0f)) ? fabsf(eya - eyb) : (2.0f - eya - eyb);
+    const float exa = erfc_pos_fast(fabsf(xa)), exb = erfc_pos_fast(fabsf(xb));
+    const float px = ((xa > 0.0f) == (xb > 0.0f)) ? fabsf(exa - exb) : (2.0f - exa - exb);
+    prob = fmaf(0.25f * px, py, prob);
+  }
+  return prob * (1.0f / 3.0f);
+}
+
 __device__ __forceinline__ float logistic_neg(float z) {  // 1 / (1 + exp(z))
   return __fdividef(1.0f, 1.0f + __expf(z));
 }
@@ -97,6 +145,108 @@ __device__ __forceinline__ float lr4s_coef(float ang, float side, float rear) {
   return c;
 }
 
+// ---- BE (be.py:66-193) shared by the summary kernels: warp-cooperative bisection on a re-timed ego path -----
+constexpr int kBeBuckets = 64;   // arc-length -> state-index lookup used by the interpolation
+struct BeView {
+  const float4* egoA;   // [T] (x, y, cos theta, sin theta)
+  const float2* egoB;   // [T] (theta, v)
+  float* dist;          // [T] cumulative chord length (be.py:99)
+  uint8_t* inv;         // [kBeBuckets + 1] last state index with dist <= b * dmax / kBeBuckets
+};
+
+static __device__ __noinline__ void be_prepare(const BeView w, int T, int lane) {
+  float carry = 0.0f;
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int i = i0 + lane;
+    float seg = 0.0f;
+    if (i >= 1 && i < T) {
+      float4 p = w.egoA[i], q = w.egoA[i - 1];
+      seg = sqrtf((p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y));
+    }
+    float sc = seg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(kFull, sc, o);
+      if (lane >= o) sc += t;
+    }
+    if (i < T) w.dist[i] = carry + sc;
+    carry += __shfl_sync(kFull, sc, 31);
+  }
+  __syncwarp();
+  const float bw = w.dist[T - 1] / (float)kBeBuckets;
+  for (int b = lane; b <= kBeBuckets; b += 32) {
+    const float q = (b == kBeBuckets) ? CUDART_INF_F : (float)b * bw;
+    int lo_j = 0, hi_j = T - 1;
+    while (lo_j < hi_j) {
+      const int mid = (lo_j + hi_j + 1) >> 1;
+      if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
+    }
+    w.inv[b] = (uint8_t)lo_j;
+  }
+  __syncwarp();
+}
+
+// lanes = time steps.  v_new[0] = v0, v_new[k+1] = max(v1 - d k dt, 0) (be.py:109); dist_new[i] = dt sum_{k<i} v_new[k]
+// (be.py:113) in closed form: the clipped arithmetic series has floor(v1 / (d dt)) + 1 positive terms.  dist_new is
+// non-decreasing in i, so scipy interp1d's bounds_error (be.py:117-124) fires iff its LAST element overruns.
+__device__ __forceinline__ float be_arclen(float dt, float v0, float v1, float step, float mpos, int i) {
+  const float m = fminf((float)(i - 1), mpos);
+  return (i == 0) ? 0.0f : dt * (v0 + fmaf(m, v1, -0.5f * step * m * (m - 1.0f)));
+}
+
+static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeView w, int a, int n_states, float hl, float hw,
+                                        float lo0, int lane, bool& range_err, unsigned& probes) {
+  const int T = k.T;
+  const int nA = min(T, n_states);
+  const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
+  const float dmax = w.dist[T - 1];
+  const float inv_w = dmax > 0.0f ? (float)kBeBuckets / dmax : 0.0f;
+  float lo = lo0, hi = 5.0f, cur = 0.0f;
+  for (int it = 0; it < 10; ++it) {
+    cur = 0.5f * (lo + hi);
+    ++probes;
+    const float step = cur * k.dt;
+    const float mpos = (step > 0.0f) ? fmaxf(floorf(__fdividef(v1, step)) + 1.0f, 0.0f) : 1.0e9f;
+    if (be_arclen(k.dt, v0, v1, step, mpos, T - 1) > dmax) { range_err = true; return CUDART_NAN_F; }
+    bool any_hit = false;
+    for (int i0 = 0; i0 < nA && !any_hit; i0 += 32) {
+      const int i = i0 + lane;
+      bool hit = false;
+      if (i < nA) {
+        const float q = be_arclen(k.dt, v0, v1, step, mpos, i);
+        // numpy.interp: j = last index with dist[j] <= q; start from the bucket's first candidate, fix a float32
+        // off-by-one of the bucket index downwards, then walk up
+        int j = w.inv[min(__float2int_rd(q * inv_w), kBeBuckets - 1)];
+        while (j > 0 && w.dist[j] > q) --j;
+        while (j < T - 1 && w.dist[j + 1] <= q) ++j;
+        const float dj = w.dist[j];
+        const float4 A0 = w.egoA[j];
+        float xn = A0.x, yn = A0.y, tn = w.egoB[j].x;
+        if (j != T - 1 && dj != q) {
+          const float4 A1 = w.egoA[j + 1];
+          const float wq = q - dj;
+          const float inv = 1.0f / (w.dist[j + 1] - dj);
+          xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
+          yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
+          tn = fmaf((w.egoB[j + 1].x - tn) * inv, wq, tn);
+        }
+        float sn, cn;
+        __sincosf(tn, &sn, &cn);
+        const float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
+        const float dx = (s0.x - xn) - k.wb * cn;
+        const float dy = (s0.y - yn) - k.wb * sn;
+        const float rx = fmaf(dx, cn, dy * sn), ry = fmaf(dy, cn, -dx * sn);
+        const float c = fmaf(cn, s0.z, sn * s0.w), s = fmaf(s0.w, cn, -s0.z * sn);
+        hit = obb_hit(rx, ry, c, s, k.hEx, k.hEy, hl, hw);
+      }
+      any_hit = __any_sync(kFull, hit);
+    }
+    if (nA > 0 && !any_hit) hi = cur; else lo = cur;   // be.py:74-77 (an agent that never exists counts as a hit)
+    if (hi - lo < 0.1f) break;                         // be.py:79
+  }
+  return cur;
+}
+
 struct EgoState {
   float x, y, th, v, c, s;
 };
@@ -104,5 +254,6 @@ struct EgoState {
 
 int launch_metric_detail(const MetricKArgs& k, int num_sms, cudaStream_t st);
 int launch_metric_flat(const MetricKArgs& k, int num_sms, cudaStream_t st);
+int launch_metric_sweep(const MetricKArgs& k, int num_sms, cudaStream_t st);
 
 }  // namespace fo

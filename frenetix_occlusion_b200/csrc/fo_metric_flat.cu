@@ -30,10 +30,9 @@ namespace fo {
 constexpr int kFlatWarps = 8;
 constexpr int kTileAgents = 256;
 constexpr int kQueueCap = 64;
-constexpr int kInvBuckets = 64;   // arc-length -> state-index lookup used by the BE interpolation
 
 __host__ __device__ inline size_t flat_warp_bytes(int T) {
-  size_t b = (size_t)kTileAgents * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kTileAgents * 4 + kQueueCap * 4 + kInvBuckets + 16;
+  size_t b = (size_t)kTileAgents * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kTileAgents * 4 + kQueueCap * 4 + kBeBuckets + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -44,7 +43,7 @@ struct WarpSmem {
   float* dist;                  // [T] cumulative chord length (BE)
   uint32_t* colfirst;           // [kTileAgents] first step with rounded distance 0 (0xffffffff = none)
   uint32_t* queue;              // [kQueueCap] gated (agent-in-tile << 8 | step) items
-  uint8_t* inv;                 // [kInvBuckets + 1] last state index with dist <= b * dmax / kInvBuckets
+  uint8_t* inv;                 // [kBeBuckets + 1] last state index with dist <= b * dmax / kBeBuckets
 };
 
 __device__ __forceinline__ WarpSmem warp_smem(unsigned char* base, int T) {
@@ -113,104 +112,6 @@ __device__ __forceinline__ void harm_logits_max(const MetricKArgs& k, const Agen
 __device__ __forceinline__ float sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
 // ---------------------------------------------------------------------------------------------
-// BE bisection for one pair, lanes = time steps (be.py:66-193); ego arrays come from shared memory.
-__device__ __noinline__ float be_bisect_flat(const MetricKArgs& k, const WarpSmem w, int a, int n_states, float hl,
-                                             float hw, float lo0, int lane, bool& range_err) {
-  const int T = k.T;
-  const int nA = min(T, n_states);
-  const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
-  const float dmax = w.dist[T - 1];
-  const float inv_w = dmax > 0.0f ? (float)kInvBuckets / dmax : 0.0f;
-  float lo = lo0, hi = 5.0f, cur = 0.0f;
-  for (int it = 0; it < 10; ++it) {
-    cur = 0.5f * (lo + hi);
-    bool hit = false, over = false;
-    // v_new[0] = v0, v_new[k+1] = max(v1 - cur*k*dt, 0) (be.py:109); dist_new[i] = dt * sum_{k<i} v_new[k]
-    // (be.py:113) in closed form: the clipped arithmetic series has mpos = floor(v1/(cur*dt)) + 1 positive terms.
-    const float step = cur * k.dt;
-    const float mpos = (step > 0.0f) ? fmaxf(floorf(__fdividef(v1, step)) + 1.0f, 0.0f) : 1.0e9f;
-    for (int i0 = 0; i0 < T; i0 += 32) {
-      const int i = i0 + lane;
-      if (i < T) {
-        const float m = fminf((float)(i - 1), mpos);                  // terms of the series included (i >= 1)
-        const float q = (i == 0) ? 0.0f : k.dt * (v0 + fmaf(m, v1, -0.5f * step * m * (m - 1.0f)));
-        if (q > dmax) over = true;            // interp1d bounds_error (be.py:117-124)
-        // numpy.interp: j = last index with dist[j] <= q.  Bracket from the arc-length lookup table,
-        // bisect inside the bracket, then guard against a float32 off-by-one in the bucket index.
-        const int b = min(__float2int_rd(q * inv_w), kInvBuckets - 1);
-        int lo_j = w.inv[b], hi_j = w.inv[b + 1];
-        while (lo_j < hi_j) {
-          const int mid = (lo_j + hi_j + 1) >> 1;
-          if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
-        }
-        while (lo_j > 0 && w.dist[lo_j] > q) --lo_j;
-        while (lo_j < T - 1 && w.dist[lo_j + 1] <= q) ++lo_j;
-        const int j = lo_j;
-        const float dj = w.dist[j];
-        float4 A0 = w.egoA[j];
-        float xn = A0.x, yn = A0.y, tn = w.egoB[j].x;
-        if (j != T - 1 && dj != q) {
-          float4 A1 = w.egoA[j + 1];
-          float wq = q - dj;
-          float inv = 1.0f / (w.dist[j + 1] - dj);
-          xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
-          yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
-          tn = fmaf((w.egoB[j + 1].x - tn) * inv, wq, tn);
-        }
-        if (i < nA) {
-          float sn, cn;
-          __sincosf(tn, &sn, &cn);
-          float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
-          float dx = (s0.x - xn) - k.wb * cn;
-          float dy = (s0.y - yn) - k.wb * sn;
-          float rx = fmaf(dx, cn, dy * sn), ry = fmaf(dy, cn, -dx * sn);
-          float c = fmaf(cn, s0.z, sn * s0.w), s = fmaf(s0.w, cn, -s0.z * sn);
-          hit |= obb_hit(rx, ry, c, s, k.hEx, k.hEy, hl, hw);
-        }
-      }
-    }
-    if (__any_sync(kFull, over)) { range_err = true; return CUDART_NAN_F; }
-    const bool any_hit = __any_sync(kFull, hit);
-    if (nA > 0 && !any_hit) hi = cur; else lo = cur;   // be.py:74-77
-    if (hi - lo < 0.1f) break;                         // be.py:79
-  }
-  return cur;
-}
-
-// cumulative chord length of the ego polyline (be.py:99) into w.dist
-__device__ __noinline__ void be_prepare(const WarpSmem w, int T, int lane) {
-  float carry = 0.0f;
-  for (int i0 = 0; i0 < T; i0 += 32) {
-    const int i = i0 + lane;
-    float seg = 0.0f;
-    if (i >= 1 && i < T) {
-      float4 p = w.egoA[i], q = w.egoA[i - 1];
-      seg = sqrtf((p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y));
-    }
-    float sc = seg;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      float t = __shfl_up_sync(kFull, sc, o);
-      if (lane >= o) sc += t;
-    }
-    if (i < T) w.dist[i] = carry + sc;
-    carry += __shfl_sync(kFull, sc, 31);
-  }
-  __syncwarp();
-  const float bw = w.dist[T - 1] / (float)kInvBuckets;
-  for (int b = lane; b <= kInvBuckets; b += 32) {
-    const float q = (b == kInvBuckets) ? CUDART_INF_F : (float)b * bw;
-    int lo_j = 0, hi_j = T - 1;
-    while (lo_j < hi_j) {
-      const int mid = (lo_j + hi_j + 1) >> 1;
-      if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
-    }
-    w.inv[b] = (uint8_t)lo_j;
-  }
-  __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------
 // MASK: compile-time metric mask (0 = read k.mmask at run time).  PRUNE: skip the exact oriented-box
 // distance when a circumcircle lower bound proves it cannot lower the lane's running minimum.
 template <uint32_t MASK, bool PRUNE, int MINB>
@@ -252,6 +153,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MINB) fo_metric_flat_kernel(c
     uint32_t flags = 0;
     bool be_ready = false;
     float be_lo0 = 0.0f;
+    const BeView bev{w.egoA, w.egoB, w.dist, w.inv};
 
     for (int a0 = 0; a0 < k.A; a0 += kTileAgents) {
       const int nAt = min(kTileAgents, k.A - a0);
@@ -337,27 +239,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MINB) fo_metric_flat_kernel(c
             const float4 s1i = __ldg(&k.tab.s1[idx]);
             const float2 s2i = __ldg(&k.tab.s2[idx]);
             const float4 Ei = w.egoA[ii];
-            // CP: 3 obstacle points x 3 axis-aligned ego boxes (collision_probability.py:94-122)
-            const float mx = s1i.z - Ei.x, my = s1i.w - Ei.y;
-            const float hx = P.hlb * s0i.z, hy = P.hlb * s0i.w;
-            const float bx = k.L3 * Ei.z, by = k.L3 * Ei.w;
-            float prob = 0.0f;
-#pragma unroll 1
-            for (int mb = 0; mb < 9; ++mb) {
-              const int m = mb / 3, bb = mb - 3 * m;
-              const float fm = (m == 0) ? 0.0f : (m == 1 ? 1.0f : -1.0f);
-              const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
-              const float ux = fmaf(fm, hx, mx), uy = fmaf(fm, hy, my);
-              const float cxb = fb * bx, cyb = fb * by;
-              // the narrow (width) factor first; a term whose factor is below 1e-10 contributes less than
-              // 1e-10 to a probability compared at an absolute floor of 2e-7 and is dropped
-              float py = half_derf((cyb - k.W2 - uy) * s2i.y, (cyb + k.W2 - uy) * s2i.y);
-              if (py > 1e-10f) {
-                float px = half_derf((cxb - k.L6 - ux) * s2i.x, (cxb + k.L6 - ux) * s2i.x);
-                prob = fmaf(px, py, prob);
-              }
-            }
-            const float cp = prob * (1.0f / 3.0f);
+            const float cp = cp_gauss_boxes(s1i.z - Ei.x, s1i.w - Ei.y, P.hlb * s0i.z, P.hlb * s0i.w, k.L3 * Ei.z,
+                                            k.L3 * Ei.w, s2i, k.L6, k.W2);
             acc_cp = fmaxf(acc_cp, cp);
             if (do_hr) {                       // risk[t] = harm[t] * cp[t], cp[t] = CP of step t+1 (hr.py:78-79)
               const float4 s0t = __ldg(&k.tab.s0[idx - 1]);
@@ -409,13 +292,14 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MINB) fo_metric_flat_kernel(c
             const int a = a0 + j0 + src;
             const AgentParams P = load_params(k.tab.prm + a);
             if (!be_ready) {
-              be_prepare(w, T, lane);
+              be_prepare(bev, T, lane);
               float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));
               be_lo0 = rintf(am * 100.0f) / 100.0f;                          // be.py:68
               be_ready = true;
             }
             bool range_err = false;
-            const float rcd = be_bisect_flat(k, w, a, P.n_states, P.hl, P.hw, be_lo0, lane, range_err);
+            unsigned probes = 0;
+            const float rcd = be_bisect(k, bev, a, P.n_states, P.hl, P.hw, be_lo0, lane, range_err, probes);
             if (range_err) flags |= FO_F_BE_RANGE;
             rcd_all = fmaxf(rcd_all, rcd);
             btn_all = fmaxf(btn_all, rcd / k.a_max);

@@ -1,0 +1,471 @@
+// Dense metric core, sm_100a -- SWEEP kernel: the throughput path for agent tables of >= one lane tile.
+//
+// Same outputs as the flat summary kernel (validity mask, 10 per-trajectory scalars, flags), different mapping:
+//
+//   * one warp owns one trajectory (persistent CTAs); its ego states live in shared memory;
+//   * LANE = AGENT, the loop runs over TIME: per-agent parameters stay in registers, the time index is
+//     warp-uniform (ego state = one broadcast LDS, no per-lane index arithmetic, no divergence on the
+//     step-range conditions) and consecutive lanes read consecutive entries of the TIME-MAJOR agent table
+//     (one coalesced 512-byte + one 128-byte request per step; the previous position the CP pairing needs,
+//     collision_probability.py:52, is simply last iteration's register);
+//   * the dense step per (trajectory, agent, step) is only *bounds*: squared centre distance vs. the running
+//     minimum (oriented-box distance needed?), squared speed difference vs. the running maximum logits
+//     (impact-angle class needed?), 5 m gate (collision probability needed?) -- about 50 instructions per 32
+//     evaluations.  Everything that passes a bound is pushed on one of two per-warp shared-memory queues and
+//     evaluated 32 items at a time with all lanes active: the exact oriented-box distance (dce.py:75-79) and/or
+//     the LR4S impact-angle logit (logistic_regression.py:35-48), and the 9-term Gaussian box mass
+//     (collision_probability.py:94-122).  No lane ever idles through a neighbour's expensive branch;
+//   * the running minimum distance and the running maximum logits are WARP-SHARED (REDUX after every drain), so
+//     a near agent found by one lane prunes the work of all 32.
+//
+// All bounds are exact (a skipped evaluation cannot change a min / max / threshold decision); results equal the
+// flat and the detail kernel.  Reference semantics: SURVEY.md appendix A; citations on the helpers in
+// fo_metric_dev.cuh.
+#include <stdlib.h>
+
+#include "fo_metric_dev.cuh"
+
+namespace fo {
+
+constexpr int kSwWarps = 8;
+constexpr int kSwTile = 256;      // agents per tile (8 lane tiles); bounds the per-warp pair arrays
+constexpr int kSwQueue = 64;
+
+__host__ __device__ inline size_t sweep_warp_bytes(int T) {
+  size_t b = (size_t)kSwTile * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kSwTile * 4 + 2 * kSwQueue * 4 + kBeBuckets + 16;
+  return (b + 15) & ~(size_t)15;
+}
+
+struct SweepSmem {
+  unsigned long long* pairkey;  // [kSwTile] (cp bits << 32 | (0xffff - t) << 16 | 1): argmax_t cp, first index on ties
+  float4* egoA;                 // [T] (x, y, cos theta, sin theta)
+  float2* egoB;                 // [T] (theta, v)
+  float* dist;                  // [T] cumulative chord length (BE)
+  uint32_t* colfirst;           // [kSwTile] first step with rounded distance 0
+  uint32_t* q_near;             // [kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
+  uint32_t* q_cp;               // [kSwQueue] (agent-in-tile << 8 | step)
+  uint8_t* inv;                 // [kBeBuckets + 1]
+};
+
+__device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T) {
+  SweepSmem w;
+  w.pairkey = reinterpret_cast<unsigned long long*>(base);
+  w.egoA = reinterpret_cast<float4*>(w.pairkey + kSwTile);
+  w.egoB = reinterpret_cast<float2*>(w.egoA + T);
+  w.dist = reinterpret_cast<float*>(w.egoB + T);
+  w.colfirst = reinterpret_cast<uint32_t*>(w.dist + T);
+  w.q_near = w.colfirst + kSwTile;
+  w.q_cp = w.q_near + kSwQueue;
+  w.inv = reinterpret_cast<uint8_t*>(w.q_cp + kSwQueue);
+  return w;
+}
+
+__device__ __forceinline__ AgentParams sw_load_params(const AgentParams* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  int4 a = __ldg(q), b = __ldg(q + 1);
+  AgentParams r;
+  r.n_states = a.x; r.model = a.y; r.hl = __int_as_float(a.z); r.hw = __int_as_float(a.w);
+  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = __int_as_float(b.w);
+  return r;
+}
+
+// order-preserving float <-> uint map (warp max of signed floats with one REDUX)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ float warp_max_signed(float v) { return ord2f(__reduce_max_sync(kFull, f2ord(v))); }
+
+__device__ __forceinline__ float sw_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+// exact harm logits for one (agent, state) -- harm_model.py:81-105, logistic_regression.py:35-48,71-73
+__device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, float ke, float ko, float dv, float dxr,
+                                               float dyr, float th, float psi, float& ze, float& zo) {
+  if (model == 0) {
+    ze = fmaf(k.hc.ia_speed * ke, dv, k.hc.ia_const);
+    zo = fmaf(k.hc.ped_speed * ko, dv, -k.hc.ped_const);
+  } else if (model == 1) {
+    const float PI_F = 3.14159265358979323846f;
+    const float rel = atan2f(dyr, dxr);
+    ze = fmaf(k.hc.rs_speed * ke, dv, k.hc.rs_const) + lr4s_coef(rel - th, k.hc.rs_side, k.hc.rs_rear);
+    zo = fmaf(k.hc.rs_speed * ko, dv, k.hc.rs_const) + lr4s_coef(PI_F + rel - psi, k.hc.rs_side, k.hc.rs_rear);
+  } else {
+    ze = CUDART_INF_F;
+    zo = CUDART_INF_F;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <uint32_t MASK, bool STATS>
+__global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int T = k.T;
+  const SweepSmem w = sweep_smem(smem_raw + (size_t)wib * sweep_warp_bytes(T), T);
+  const int warp0 = blockIdx.x * kSwWarps + wib;
+  const int nwarps = gridDim.x * kSwWarps;
+  const uint32_t mm = MASK ? MASK : k.mmask;
+  const bool do_cp = mm & FO_M_CP, do_dce = mm & FO_M_DCE, do_hr = mm & FO_M_HR, do_be = mm & FO_M_BE,
+             do_ttc = mm & FO_M_TTC;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float rE = sqrtf(k.hEx * k.hEx + k.hEy * k.hEy);   // ego circumradius
+  const float cmax = fmaxf(0.0f, fmaxf(k.hc.rs_side, k.hc.rs_rear));
+  const int Ap = k.tab.Ap;
+  unsigned long long st_dense = 0, st_obb = 0, st_lr = 0, st_cp = 0, st_be = 0, st_probe = 0;
+
+  for (int n = warp0; n < k.N; n += nwarps) {
+    // ---- stage the ego trajectory --------------------------------------------------------------
+    float amin = 0.0f;
+    const float* eg = k.ego + (size_t)n * T * 5;
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      float x = __ldg(eg + i * 5 + 0), y = __ldg(eg + i * 5 + 1), th = __ldg(eg + i * 5 + 2);
+      float v = __ldg(eg + i * 5 + 3);
+      amin = fminf(amin, __ldg(eg + i * 5 + 4));
+      float sn, cs;
+      sincosf(th, &sn, &cs);
+      w.egoA[i] = make_float4(x, y, cs, sn);
+      w.egoB[i] = make_float2(th, v);
+    }
+    __syncwarp();
+
+    uint32_t rmin = 0xffffffu;                       // warp-uniform running min of round(d * 1000)
+    float zb_e = -CUDART_INF_F, zb_o = -CUDART_INF_F; // warp-uniform running maxima of the harm logits
+    uint32_t acc_col = 0xffffffffu;
+    float acc_ze = -CUDART_INF_F, acc_zo = -CUDART_INF_F;
+    float acc_er = 0.0f, acc_or = 0.0f, acc_cp = 0.0f, acc_hwc = 0.0f;
+    float btn_all = 0.0f, rcd_all = 0.0f;
+    uint32_t flags = 0;
+    bool be_ready = false;
+    float be_lo0 = 0.0f;
+
+    const BeView bev{w.egoA, w.egoB, w.dist, w.inv};
+
+    for (int a0 = 0; a0 < k.A; a0 += kSwTile) {
+      const int nAt = min(kSwTile, k.A - a0);
+      for (int j = lane; j < nAt; j += 32) { w.pairkey[j] = 0ull; w.colfirst[j] = 0xffffffffu; }
+      __syncwarp();
+      int qn = 0, qc = 0;
+      // per-lane bound state of the current lane tile (refreshed after every drain)
+      float lim0 = 0.0f, lim2 = 0.0f, thr2 = CUDART_INF_F;
+      float kse = 0.0f, kso = 0.0f, kce = 0.0f, kco = 0.0f;
+      bool is_m1 = false;
+
+      // distance >= |centres| - rE - rO: the exact box distance is needed only while that bound can still lower
+      // the running minimum (+2 units of the 1 mm rounding grid)
+      auto upd_lim = [&]() {
+        const float lim = lim0 + (float)(rmin + 2u) * 0.001f;
+        lim2 = lim * lim;
+      };
+      // LR4S logit <= ks dv + kc + cmax: the impact-angle class is needed only while that can still raise a
+      // running maximum, i.e. dv^2 > thr2 (slightly lowered so float rounding can only add work)
+      auto upd_thr = [&]() {
+        float t2 = CUDART_INF_F;
+        if (is_m1) {
+          const float ze_m = fmaxf(zb_e, acc_ze), zo_m = fmaxf(zb_o, acc_zo);
+          const float te = (kse > 0.0f) ? __fdividef(ze_m - cmax - kce, kse) : ((kce + cmax > ze_m) ? -1.0f : CUDART_INF_F);
+          const float to = (kso > 0.0f) ? __fdividef(zo_m - cmax - kco, kso) : ((kco + cmax > zo_m) ? -1.0f : CUDART_INF_F);
+          const float tm = fminf(te, to);
+          t2 = (tm > 0.0f) ? tm * tm * 0.99999f : -1.0f;
+        }
+        thr2 = t2;
+      };
+
+      // ---- drains: 32 queued items at a time, all lanes active -------------------------------------------
+      auto drain_near = [&](int cnt) {
+        uint32_t item = 0;
+        if (lane < cnt) item = w.q_near[qn - cnt + lane];
+        qn -= cnt;
+        __syncwarp();
+        uint32_t r = 0xffffffu;
+        if (lane < cnt) {
+          const int ial = (int)((item >> 8) & 0xffffu), ii = (int)(item & 0xffu);
+          const int a = a0 + ial;
+          const float4 s0 = __ldg(&k.tab.t0[(size_t)ii * Ap + a]);
+          const float4 EA = w.egoA[ii];
+          const float c = fmaf(EA.z, s0.z, EA.w * s0.w), s = fmaf(s0.w, EA.z, -s0.z * EA.w);
+          const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
+          if (item & 0x40000000u) {            // exact oriented-box distance, np.round(d, 3) (dce.py:75-79)
+            const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
+            const float dx = dxr - k.wb * EA.z, dy = dyr - k.wb * EA.w;
+            const float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
+            const float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, __int_as_float(pa.z), __int_as_float(pa.w)));
+            r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);
+            if (r == 0u) atomicMin(&w.colfirst[ial], (uint32_t)ii);
+            if (STATS) ++st_obb;
+          }
+          if (item & 0x80000000u) {            // LR4S logits with the impact-angle class (protected agents)
+            const int4 pb = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a) + 1);
+            const float4 s1 = __ldg(&k.tab.s1[(size_t)a * k.Tp + ii]);
+            const float2 EB = w.egoB[ii];
+            const float dv2 = fmaxf(fmaf(EB.y, EB.y, s1.y * s1.y) - 2.0f * EB.y * s1.y * c, 0.0f);
+            const float dv = dv2 * rsqrtf(fmaxf(dv2, 1e-30f));
+            float ze, zo;
+            sw_harm_logits(k, 1, __int_as_float(pb.y), __int_as_float(pb.z), dv, dxr, dyr, EB.x, s1.x, ze, zo);
+            acc_ze = fmaxf(acc_ze, ze);
+            acc_zo = fmaxf(acc_zo, zo);
+            if (STATS) ++st_lr;
+          }
+        }
+        rmin = min(rmin, __reduce_min_sync(kFull, r));
+        zb_e = fmaxf(zb_e, warp_max_signed(acc_ze));
+        zb_o = fmaxf(zb_o, warp_max_signed(acc_zo));
+        upd_lim();
+        upd_thr();
+      };
+      auto drain_cp = [&](int cnt) {
+        uint32_t item = 0;
+        if (lane < cnt) item = w.q_cp[qc - cnt + lane];
+        qc -= cnt;
+        __syncwarp();
+        if (lane < cnt) {
+          const int ial = (int)(item >> 8), ii = (int)(item & 0xffu), t = ii - 1;
+          const int a = a0 + ial;
+          const AgentParams P = sw_load_params(k.tab.prm + a);
+          const size_t idx = (size_t)a * k.Tp + ii;
+          const float4 s0i = __ldg(&k.tab.s0[idx]);
+          const float4 s1i = __ldg(&k.tab.s1[idx]);
+          const float2 s2i = __ldg(&k.tab.s2[idx]);
+          const float4 Ei = w.egoA[ii];
+          const float cp = cp_gauss_boxes(s1i.z - Ei.x, s1i.w - Ei.y, P.hlb * s0i.z, P.hlb * s0i.w, k.L3 * Ei.z,
+                                          k.L3 * Ei.w, s2i, k.L6, k.W2);
+          acc_cp = fmaxf(acc_cp, cp);
+          if (do_hr) {                       // risk[t] = harm[t] * cp[t], cp[t] = CP of step t+1 (hr.py:78-79)
+            const float4 s0t = __ldg(&k.tab.s0[idx - 1]);
+            const float4 s1t = __ldg(&k.tab.s1[idx - 1]);
+            const float4 Et = w.egoA[t];
+            const float2 EtB = w.egoB[t];
+            const float ct = fmaf(Et.z, s0t.z, Et.w * s0t.w);
+            const float dv = sqrtf(fmaxf(fmaf(EtB.y, EtB.y, s1t.y * s1t.y) - 2.0f * EtB.y * s1t.y * ct, 0.0f));
+            float ze, zo;
+            sw_harm_logits(k, P.model, P.ke, P.ko, dv, s0t.x - Et.x, s0t.y - Et.y, EtB.x, s1t.x, ze, zo);
+            acc_er = fmaxf(acc_er, sw_sigmoid(ze) * cp);
+            acc_or = fmaxf(acc_or, sw_sigmoid(zo) * cp);
+            if (cp > 0.01f)                  // candidates for obst_harm[argmax cp] (hr.py:81-84)
+              atomicMax(&w.pairkey[ial], ((unsigned long long)__float_as_uint(cp) << 32) |
+                                             ((unsigned long long)(0xffffu - (unsigned)t) << 16) | 1ull);
+          }
+          if (STATS) ++st_cp;
+        }
+        __syncwarp();
+      };
+
+      // ---- dense sweep: lane tiles of 32 agents x T steps -------------------------------------------------
+      for (int sub = 0; sub < nAt; sub += 32) {
+        const int al = sub + lane;
+        const int a = a0 + al;
+        const bool alive = al < nAt;
+        AgentParams P;
+        P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
+        if (alive) P = sw_load_params(k.tab.prm + a);
+        const int nS = P.n_states;                        // this agent exists at steps [0, nS)
+        const int nH = min(nS, T - 1);                    // harm is evaluated at steps [0, min(T-1, nS))
+        const int iend = min(T, (int)__reduce_max_sync(kFull, (unsigned)nS));
+        const bool is_m0 = P.model == 0;
+        is_m1 = P.model == 1;
+        // harm logit = ks * dv + kc (+ LR4S class coefficient for protected agents)
+        kse = (is_m0 ? k.hc.ia_speed : k.hc.rs_speed) * P.ke;
+        kso = (is_m0 ? k.hc.ped_speed : k.hc.rs_speed) * P.ko;
+        kce = is_m0 ? k.hc.ia_const : k.hc.rs_const;
+        kco = is_m0 ? -k.hc.ped_const : k.hc.rs_const;
+        if (do_hr && alive && P.model == 2 && nH > 0) { acc_ze = CUDART_INF_F; acc_zo = CUDART_INF_F; }
+        lim0 = rE + P.pad;
+        upd_lim();
+        upd_thr();
+        const float hlb2 = P.hlb * P.hlb, hlbm2 = -2.0f * P.hlb;
+        const uint32_t item0 = (uint32_t)al << 8;
+        const float4* t0 = k.tab.t0 + a0 + sub + lane;     // padded to a multiple of 32 agents: always in bounds
+        const float* tv = k.tab.tv + a0 + sub + lane;
+        float pxp = 0.0f, pyp = 0.0f;                      // position at i-1 (collision_probability.py:52)
+        float acc_dv2 = 0.0f;                              // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
+        for (int i = 0; i < iend; ++i, t0 += Ap, tv += Ap) {
+          const float4 EA = w.egoA[i];
+          const float ve = w.egoB[i].y;
+          const float4 s0 = __ldg(t0);
+          const float va = __ldg(tv);
+          const bool live = i < nS;
+          const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
+          bool need_obb = false, need_lr = false, ingate = false;
+          if (do_dce) {
+            const float dx = fmaf(-k.wb, EA.z, dxr), dy = fmaf(-k.wb, EA.w, dyr);   // centre to centre
+            need_obb = live & (fmaf(dx, dx, dy * dy) < lim2);
+          }
+          if (do_hr) {
+            const float c = fmaf(EA.z, s0.z, EA.w * s0.w);                            // cos(yaw - theta)
+            const float dv2 = fmaxf(fmaf(-2.0f * ve * va, c, fmaf(ve, ve, va * va)), 0.0f);
+            const bool live_h = i < nH;
+            if (live_h) acc_dv2 = fmaxf(acc_dv2, dv2);
+            need_lr = live_h & (dv2 > thr2);
+          }
+          if (do_cp) {                                                                // 5 m gate, collision_probability.py:61-78
+            // min over the points p, p +- h u of |. - e|^2  =  |m|^2 + min(0, h^2 - 2 h |m.u|),  m = p_{i-1} - e_i
+            const float mx = pxp - EA.x, my = pyp - EA.y;
+            const float mu = fmaf(mx, s0.z, my * s0.w);
+            const float dmin = fmaf(mx, mx, my * my) + fminf(fmaf(hlbm2, fabsf(mu), hlb2), 0.0f);
+            ingate = live & (i >= 1) & (dmin <= 25.0f);
+          }
+          pxp = s0.x; pyp = s0.y;
+          const bool near = need_obb | need_lr;
+          unsigned b = __ballot_sync(kFull, near);
+          if (b) {
+            if (near) w.q_near[qn + __popc(b & lt_mask)] = item0 | (uint32_t)i | (need_obb ? 0x40000000u : 0u) |
+                                                         (need_lr ? 0x80000000u : 0u);
+            qn += __popc(b);
+            __syncwarp();
+            if (qn >= 32) drain_near(32);
+          }
+          b = __ballot_sync(kFull, ingate);
+          if (b) {
+            if (ingate) w.q_cp[qc + __popc(b & lt_mask)] = item0 | (uint32_t)i;
+            qc += __popc(b);
+            __syncwarp();
+            if (qc >= 32) drain_cp(32);
+          }
+          if (STATS) st_dense += live;
+        }
+        if (do_hr && is_m0 && nH > 0) {
+          const float dvm = acc_dv2 * rsqrtf(fmaxf(acc_dv2, 1e-30f));
+          acc_ze = fmaxf(acc_ze, fmaf(kse, dvm, kce));
+          acc_zo = fmaxf(acc_zo, fmaf(kso, dvm, kco));
+        }
+        if (do_hr) {
+          zb_e = fmaxf(zb_e, warp_max_signed(acc_ze));
+          zb_o = fmaxf(zb_o, warp_max_signed(acc_zo));
+        }
+      }
+      // ---- flush the queues of this agent tile -------------------------------------------------------------
+      is_m1 = false;
+      while (qn > 0) drain_near(min(qn, 32));
+      while (qc > 0) drain_cp(min(qc, 32));
+      __syncwarp();
+
+      // ---- tile epilogue: harm_with_cp, wttc, BE --------------------------------------------------------------
+      for (int j0 = 0; j0 < nAt; j0 += 32) {
+        const int j = j0 + lane;
+        const unsigned long long key = (j < nAt) ? w.pairkey[j] : 0ull;
+        const uint32_t cf = (j < nAt) ? w.colfirst[j] : 0xffffffffu;
+        if (key != 0ull) {
+          const int t = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
+          const int a = a0 + j;
+          const AgentParams P = sw_load_params(k.tab.prm + a);
+          const size_t idx = (size_t)a * k.Tp + t;
+          const float4 s0t = __ldg(&k.tab.s0[idx]);
+          const float4 s1t = __ldg(&k.tab.s1[idx]);
+          const float4 Et = w.egoA[t];
+          const float2 EtB = w.egoB[t];
+          const float ct = fmaf(Et.z, s0t.z, Et.w * s0t.w);
+          const float dv = sqrtf(fmaxf(fmaf(EtB.y, EtB.y, s1t.y * s1t.y) - 2.0f * EtB.y * s1t.y * ct, 0.0f));
+          float ze, zo;
+          sw_harm_logits(k, P.model, P.ke, P.ko, dv, s0t.x - Et.x, s0t.y - Et.y, EtB.x, s1t.x, ze, zo);
+          acc_hwc = fmaxf(acc_hwc, sw_sigmoid(zo));
+        }
+        if (do_ttc) acc_col = min(acc_col, cf);
+        if (do_be && do_ttc) {
+          unsigned m = __ballot_sync(kFull, cf != 0xffffffffu && cf > 0u);   // be.py:49-50
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int a = a0 + j0 + src;
+            const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
+            if (!be_ready) {
+              be_prepare(bev, T, lane);
+              float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));
+              be_lo0 = rintf(am * 100.0f) / 100.0f;                          // be.py:68
+              be_ready = true;
+            }
+            bool range_err = false;
+            unsigned probes = 0;
+            const float rcd = be_bisect(k, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane,
+                                        range_err, probes);
+            if (range_err) flags |= FO_F_BE_RANGE;
+            rcd_all = fmaxf(rcd_all, rcd);
+            btn_all = fmaxf(btn_all, rcd / k.a_max);
+            if (STATS && lane == 0) { st_be += 1; st_probe += probes; }
+          }
+        }
+      }
+      __syncwarp();
+    }  // agent tiles
+
+    // ---- per-trajectory reduction and threshold mask (metric.py:50-98) ----------------------------------
+    const float er = umaxf(acc_er), orr = umaxf(acc_or), cpm = umaxf(acc_cp), hwc_all = umaxf(acc_hwc);
+    const float ze = warp_max_signed(acc_ze), zo = warp_max_signed(acc_zo);
+    const uint32_t col = __reduce_min_sync(kFull, acc_col);
+    if (lane == 0) {
+      const float eh = sw_sigmoid(ze), oh = sw_sigmoid(zo);   // logistic is monotone: max harm = logistic(max logit)
+      const bool has_agents = k.A > 0 && mm != 0;
+      const double dce_min = (double)rmin / 1000.0;
+      const bool has_col = col != 0xffffffffu;
+      const double wttc = has_col ? rint((double)col * k.dtd * 1000.0) / 1000.0 : (double)CUDART_INF;
+      bool ok = true;
+      if (has_agents) {
+        if (do_be && (k.tmask & FO_T_BE) && (double)btn_all > k.thr_be) ok = false;
+        if (do_hr && (k.tmask & FO_T_HARM) && (double)hwc_all > k.thr_harm) ok = false;
+        if (do_hr && (k.tmask & FO_T_RISK) && (double)orr > k.thr_risk) ok = false;
+        if (do_hr && (k.tmask & FO_T_CP) && (double)cpm > k.thr_cp) ok = false;
+        if (do_ttc && (k.tmask & FO_T_TTC) && has_col && wttc < k.thr_ttc) ok = false;
+        if (do_dce && (k.tmask & FO_T_DCE) && rmin != 0xffffffu && dce_min < k.thr_dce) ok = false;
+        if (flags & FO_F_BE_RANGE) ok = false;
+      }
+      k.valid[n] = ok ? 1 : 0;
+      if (k.flags) k.flags[n] = flags;
+      if (k.summary) {
+        float* sm = k.summary + (size_t)n * FO_SUMMARY_K;
+        sm[0] = er; sm[1] = orr; sm[2] = do_hr ? eh : 0.0f; sm[3] = do_hr ? oh : 0.0f; sm[4] = cpm; sm[5] = hwc_all;
+        sm[6] = (rmin == 0xffffffu || !do_dce) ? CUDART_INF_F : (float)dce_min;
+        sm[7] = has_col ? (float)wttc : CUDART_INF_F;
+        sm[8] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : btn_all;
+        sm[9] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd_all;
+      }
+    }
+  }
+  if (STATS && k.stats) {
+    auto wsum = [&](unsigned long long v) {
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      return v;
+    };
+    const unsigned long long s0 = wsum(st_dense), s1 = wsum(st_obb), s2 = wsum(st_lr), s3 = wsum(st_cp);
+    st_be = wsum(st_be); st_probe = wsum(st_probe);
+    if (lane == 0) {
+      atomicAdd(&k.stats[0], s0); atomicAdd(&k.stats[1], s1); atomicAdd(&k.stats[2], s2); atomicAdd(&k.stats[3], s3);
+      atomicAdd(&k.stats[4], st_be); atomicAdd(&k.stats[5], st_probe);
+    }
+  }
+}
+
+template <uint32_t MASK, bool STATS>
+static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st) {
+  const size_t smem = sweep_warp_bytes(k.T) * kSwWarps;
+  static size_t configured = 0;
+  static int per_sm = 1;
+  if (smem != configured) {
+    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS>,
+                                                              kSwWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    configured = smem;
+  }
+  const int ctas_needed = (k.N + kSwWarps - 1) / kSwWarps;
+  const int full = num_sms * per_sm;
+  const int grid = ctas_needed < full ? ctas_needed : full;   // persistent: warps stride over trajectories
+  fo_metric_sweep_kernel<MASK, STATS><<<grid, kSwWarps * 32, smem, st>>>(k);
+  count_launch();
+  FO_CUDA_TRY(cudaGetLastError());
+  return FO_OK;
+}
+
+int launch_metric_sweep(const MetricKArgs& k, int num_sms, cudaStream_t st) {
+  constexpr uint32_t kAll = FO_M_CP | FO_M_DCE | FO_M_TTC | FO_M_HR | FO_M_BE | FO_M_TTCE | FO_M_WTTC;
+  constexpr uint32_t kDefault = kAll & ~FO_M_BE;   // occlusion.yaml:12-18
+  if (k.stats) return launch_sweep_inst<0u, true>(k, num_sms, st);
+  if (k.mmask == kAll) return launch_sweep_inst<kAll, false>(k, num_sms, st);
+  if (k.mmask == kDefault) return launch_sweep_inst<kDefault, false>(k, num_sms, st);
+  return launch_sweep_inst<0u, false>(k, num_sms, st);
+}
+
+}  // namespace fo

@@ -227,6 +227,37 @@ class MetricEngine:
         host = torch.from_numpy(arr.astype(np.float32)).pin_memory()
         return host.to(self.device, non_blocking=True)
 
+    def _args(self, t, out):
+        N, T = int(t.shape[0]), int(t.shape[1])
+        a = L.FoMetricArgs()
+        a.ego, a.n_traj, a.n_states = t.data_ptr(), N, T
+        a.agent_table = self._table.data_ptr() if self._table is not None else None
+        a.n_agents, a.t_stride = self.n_agents, max(self.t_stride, 1)
+        a.vehicle, a.harm, a.dt = self.vehicle, self.harm, self.dt
+        a.metric_mask, a.threshold_mask = self.metric_mask, self.threshold_mask
+        for name in L.T_BITS:
+            v = self.thresholds.get(name)
+            setattr(a, "thr_" + name, float(v) if v is not None else 0.0)
+        a.valid, a.summary, a.flags = out.valid.data_ptr(), out.summary.data_ptr(), out.flags.data_ptr()
+        return a
+
+    def work_stats(self, ego) -> dict:
+        """How much of the algorithmic work survives the exact bounds (``fo_metric_stats``): counts of visited
+        (trajectory, agent, step) evaluations, exact box distances, LR4S logits, CP evaluations, BE bisections and
+        probes for one pass over ``ego``.  Used by bench.py's flop model; synchronises."""
+        t = self.to_device_bundle(ego)
+        N = int(t.shape[0])
+        dev = self.device
+        with torch.cuda.device(dev):
+            out = BundleResult(torch.empty(N, dtype=torch.uint8, device=dev),
+                               torch.empty((N, L.FO_SUMMARY_K), dtype=torch.float32, device=dev),
+                               torch.empty(N, dtype=torch.int32, device=dev))
+            a = self._args(t, out)
+            cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+            L.check(L.lib.fo_metric_stats(C.byref(a), C.c_void_p(cnt.data_ptr()), self._stream()), "fo_metric_stats")
+            c = cnt.cpu().tolist()
+        return {"visited": c[0], "obb": c[1], "lr4s": c[2], "cp": c[3], "be": c[4], "be_probes": c[5]}
+
     def assess(self, ego, want_pair: bool = False, want_step: bool = False, out: Optional[BundleResult] = None
                ) -> BundleResult:
         """One pass of the dense core over a trajectory bundle (asynchronous on the current stream)."""

@@ -142,6 +142,14 @@ typedef struct FoMetricArgs {
  * (cp.py, dce.py, ttc.py, ttce.py, wttc.py, hr.py, be.py, metrics/utils/*.py) for a whole bundle. */
 int fo_metric_bundle(const FoMetricArgs *args, void *stream);
 
+/* Work counters of one pass of the summary path over the bundle (same arguments as fo_metric_bundle, pair and
+ * step must be NULL): how much of the algorithmic work survives the exact bounds.  bench.py uses them for the
+ * flop model behind roofline.achieved.  counters_dev[FO_STATS_K] (device, zeroed by the call) =
+ * { (trajectory, agent, step) evaluations visited, exact oriented-box distances, LR4S impact-angle logits,
+ *   collision-probability evaluations (inside the 5 m gate), BE bisections, BE probes, 0, 0 }. */
+#define FO_STATS_K 8
+int fo_metric_stats(const FoMetricArgs *args, uint64_t *counters_dev, void *stream);
+
 /* Same computation driven from HOST buffers (pinned or pageable): copies ego / agents to the
  * device, runs fo_agents_pack + fo_metric_bundle, copies valid/summary/flags back and synchronises.
  * This is the call a non-torch embedder of the reference would make; device workspace is owned by

@@ -103,8 +103,9 @@ def test_summary_kernel_equals_detail_kernel(cuda_device):
         assert np.array_equal(res_d["summary"][:, col], res_s["summary"][:, col])
     be_same = res_d["summary"][ok, 9] == res_s["summary"][ok, 9]     # bisection ties (one probe flips)
     assert (~be_same).sum() <= max(2, 0.005 * ok.sum()), int((~be_same).sum())
+    # the summary kernels use the 18-instruction erfc (4e-6 relative in float32), the detail kernel CUDA's erfcf
     for col in range(6):
-        np.testing.assert_allclose(res_s["summary"][:, col], res_d["summary"][:, col], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(res_s["summary"][:, col], res_d["summary"][:, col], rtol=3e-5, atol=1e-7)
     ok = (res_d["flags"] & 1) == 0
     # and the summary is the reduction of the per-pair detail
     p = res_d["pair"]
