@@ -278,18 +278,30 @@ class MetricEngine:
                     out.pair = torch.empty((N, A, L.FO_PAIR_K), dtype=torch.float32, device=dev)
                 if want_step:
                     out.step = torch.empty((N, A, max(T - 1, 0), L.FO_STEP_K), dtype=torch.float32, device=dev)
-            a = L.FoMetricArgs()
-            a.ego, a.n_traj, a.n_states = t.data_ptr(), N, T
-            a.agent_table = self._table.data_ptr() if self._table is not None else None
-            a.n_agents, a.t_stride = A, max(self.t_stride, 1)
-            a.vehicle, a.harm, a.dt = self.vehicle, self.harm, self.dt
-            a.metric_mask, a.threshold_mask = self.metric_mask, self.threshold_mask
-            for name in L.T_BITS:
-                v = self.thresholds.get(name)
-                setattr(a, "thr_" + name, float(v) if v is not None else 0.0)
-            a.valid, a.summary, a.flags = out.valid.data_ptr(), out.summary.data_ptr(), out.flags.data_ptr()
+            a = self._args(t, out)
             a.pair = out.pair.data_ptr() if (out.pair is not None and A > 0) else None
             a.step = out.step.data_ptr() if (out.step is not None and A > 0 and T > 1) else None
             L.check(L.lib.fo_metric_bundle(C.byref(a), self._stream()), "fo_metric_bundle")
         out._keepalive = t
         return out
+
+    def capture(self, ego_dev: torch.Tensor, out: Optional[BundleResult] = None):
+        """CUDA-graph form of ``assess`` for the per-planning-step latency path: the launch on a device-resident
+        bundle (fixed address and shape; refill it in place before every replay) is captured once, ``replay()``
+        re-issues it without any per-call host work.  Returns ``(graph, out)``."""
+        if not (isinstance(ego_dev, torch.Tensor) and ego_dev.is_cuda and ego_dev.dtype == torch.float32
+                and ego_dev.is_contiguous()):
+            raise ValueError("capture() needs a contiguous float32 CUDA tensor [N, T, 5]")
+        N = int(ego_dev.shape[0])
+        dev = self.device
+        with torch.cuda.device(dev):
+            if out is None:
+                out = BundleResult(torch.empty(N, dtype=torch.uint8, device=dev),
+                                   torch.empty((N, L.FO_SUMMARY_K), dtype=torch.float32, device=dev),
+                                   torch.empty(N, dtype=torch.int32, device=dev))
+            self.assess(ego_dev, out=out)                  # warm-up outside the capture (first-use attribute calls)
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.assess(ego_dev, out=out)
+        return g, out
