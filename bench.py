@@ -295,7 +295,7 @@ def run_ours(args):
     evals_local = n_local * A * (T - 1)
     achieved_tflops = evals_local * flop_per_eval / (k_ms * 1e-3) / 1e12
     alg_bytes = n_local * (T * 5 * 4 + 1 + 4 + 4 * L.FO_SUMMARY_K) + A * T * 32
-    roofline = {"bound": "fp32", "kernel": "fo_metric_sweep_kernel" if A >= 96 else "fo_metric_flat/sweep (by agent count)", "achieved": achieved_tflops, "peak": peak_tflops,
+    roofline = {"bound": "fp32", "kernel": "fo_metric_sweep_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
                 "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "peak_source": peak_src,
                 "kernel_ms": k_ms, "flop_per_eval": flop_per_eval, "gate_fraction": g_frac, "be_pair_fraction": be_pairs,
                 "traffic": None,

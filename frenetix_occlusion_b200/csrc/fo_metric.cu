@@ -155,12 +155,5 @@ static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, 
 
   cudaStream_t st = (cudaStream_t)stream;
   if (k.pair || k.step) return fo::launch_metric_detail(k, g_num_sms, st);
-  // summary path: lane = agent sweep when a 32-agent lane tile is reasonably full, else the flattened
-  // (agent x step) mapping that keeps every lane busy for a handful of agents (the planner's usual case)
-  static const bool force_flat = getenv("FO_FORCE_FLAT") != nullptr;     // measurement switches
-  static const bool force_sweep = getenv("FO_FORCE_SWEEP") != nullptr;
-  const int lanes_used = k.A % 32 == 0 ? 32 : k.A % 32;
-  const bool sweep_ok = k.A >= 24 && (k.A >= 96 || lanes_used >= 24);
-  if (((sweep_ok || force_sweep) && !force_flat) || stats) return fo::launch_metric_sweep(k, g_num_sms, st);
-  return fo::launch_metric_flat(k, g_num_sms, st);
+  return fo::launch_metric_sweep(k, g_num_sms, st);
 }

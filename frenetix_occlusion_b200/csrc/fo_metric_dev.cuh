@@ -201,6 +201,11 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
   const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
   const float dmax = w.dist[T - 1];
   const float inv_w = dmax > 0.0f ? (float)kBeBuckets / dmax : 0.0f;
+  // the agent's states do not depend on the probe: the first two 32-step chunks stay in registers for the whole
+  // bisection (covers T <= 64, i.e. every horizon the reference uses), later chunks are re-read per probe
+  const float4* sa = k.tab.s0 + (size_t)a * k.Tp;
+  const float4 pre0 = (lane < nA) ? __ldg(sa + lane) : make_float4(0, 0, 1, 0);
+  const float4 pre1 = (32 + lane < nA) ? __ldg(sa + 32 + lane) : make_float4(0, 0, 1, 0);
   float lo = lo0, hi = 5.0f, cur = 0.0f;
   for (int it = 0; it < 10; ++it) {
     cur = 0.5f * (lo + hi);
@@ -232,7 +237,7 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
         }
         float sn, cn;
         __sincosf(tn, &sn, &cn);
-        const float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
+        const float4 s0 = (i0 == 0) ? pre0 : ((i0 == 32) ? pre1 : __ldg(sa + i));
         const float dx = (s0.x - xn) - k.wb * cn;
         const float dy = (s0.y - yn) - k.wb * sn;
         const float rx = fmaf(dx, cn, dy * sn), ry = fmaf(dy, cn, -dx * sn);
@@ -253,7 +258,6 @@ struct EgoState {
 
 
 int launch_metric_detail(const MetricKArgs& k, int num_sms, cudaStream_t st);
-int launch_metric_flat(const MetricKArgs& k, int num_sms, cudaStream_t st);
 int launch_metric_sweep(const MetricKArgs& k, int num_sms, cudaStream_t st);
 
 }  // namespace fo

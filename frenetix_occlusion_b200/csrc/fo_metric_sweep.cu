@@ -1,38 +1,50 @@
-// Dense metric core, sm_100a -- SWEEP kernel: the throughput path for agent tables of >= one lane tile.
+// Dense metric core, sm_100a -- the SUMMARY kernel (throughput sweeps and the per-planning-step latency case).
 //
-// Same outputs as the flat summary kernel (validity mask, 10 per-trajectory scalars, flags), different mapping:
+// Emits what the planner consumes per trajectory: the validity mask (metrics/metric.py:50-98), ten summary scalars
+// and the flags.  Mapping (B200-first, not a translation of the reference's Python loops):
 //
-//   * one warp owns one trajectory (persistent CTAs); its ego states live in shared memory;
-//   * LANE = AGENT, the loop runs over TIME: per-agent parameters stay in registers, the time index is
-//     warp-uniform (ego state = one broadcast LDS, no per-lane index arithmetic, no divergence on the
-//     step-range conditions) and consecutive lanes read consecutive entries of the TIME-MAJOR agent table
-//     (one coalesced 512-byte + one 128-byte request per step; the previous position the CP pairing needs,
-//     collision_probability.py:52, is simply last iteration's register);
-//   * the dense step per (trajectory, agent, step) is only *bounds*: squared centre distance vs. the running
-//     minimum (oriented-box distance needed?), squared speed difference vs. the running maximum logits
-//     (impact-angle class needed?), 5 m gate (collision probability needed?) -- about 50 instructions per 32
-//     evaluations.  Everything that passes a bound is pushed on one of two per-warp shared-memory queues and
-//     evaluated 32 items at a time with all lanes active: the exact oriented-box distance (dce.py:75-79) and/or
-//     the LR4S impact-angle logit (logistic_regression.py:35-48), and the 9-term Gaussian box mass
-//     (collision_probability.py:94-122).  No lane ever idles through a neighbour's expensive branch;
-//   * the running minimum distance and the running maximum logits are WARP-SHARED (REDUX after every drain), so
-//     a near agent found by one lane prunes the work of all 32.
+//   * one CTA = one TEAM of W warps owns one trajectory (persistent: teams stride over the bundle); its T ego states
+//     are staged once in shared memory.  W = 1 for sweeps that oversubscribe the machine; W up to 8 when the whole
+//     bundle fits in one wave, because then the latency of a bundle is the critical path of its slowest trajectory;
+//   * LANE = (AGENT, TIME SLICE), the loop runs over the steps of the slice: with >= 32 agents a warp holds 32 agents
+//     and one slice (the time index is warp-uniform, the ego state one broadcast LDS); with fewer agents the 32 lanes
+//     are 32/A' slices x A' agents, so all lanes stay busy for the planner's usual handful of phantom agents.
+//     Per-agent parameters stay in registers, consecutive lanes read consecutive entries of the TIME-MAJOR agent
+//     table (coalesced), and the previous position the CP pairing needs (collision_probability.py:52) is simply last
+//     iteration's register;
+//   * the dense step per (trajectory, agent, step) is only *bounds*: squared centre distance vs. the running minimum
+//     (oriented-box distance needed?), squared speed difference vs. the running maximum logits (impact-angle class
+//     needed?), 5 m gate (collision probability needed?) -- about 50 instructions per 32 evaluations.  Everything
+//     that passes a bound is pushed on one of two per-warp shared-memory queues and evaluated 32 items at a time with
+//     all lanes active: the exact oriented-box distance (dce.py:75-79) and/or the LR4S impact-angle logit
+//     (logistic_regression.py:35-48), and the 9-term Gaussian box mass (collision_probability.py:94-122).  What is
+//     left in the queues at the end of an agent tile is pooled across the team and drained cooperatively;
+//   * the running minimum distance and the running maximum logits are WARP-SHARED (REDUX after every drain), so a
+//     near agent found by one lane prunes the work of all 32;
+//   * colliding pairs are collected in a team list and their BE bisections (be.py:66-193) are dealt round-robin to
+//     the warps; per-trajectory results are order-independent min/max reductions (lane -> warp REDUX -> team).
 //
-// All bounds are exact (a skipped evaluation cannot change a min / max / threshold decision); results equal the
-// flat and the detail kernel.  Reference semantics: SURVEY.md appendix A; citations on the helpers in
-// fo_metric_dev.cuh.
+// All bounds are exact (a skipped evaluation cannot change a min / max / threshold decision); results equal the detail
+// kernel's.  Reference semantics: SURVEY.md appendix A; citations on the helpers in fo_metric_dev.cuh.
 #include <stdlib.h>
 
 #include "fo_metric_dev.cuh"
 
 namespace fo {
 
-constexpr int kSwWarps = 8;
-constexpr int kSwTile = 256;      // agents per tile (8 lane tiles); bounds the per-warp pair arrays
+constexpr int kSwMaxWarps = 8;
+constexpr int kSwTile = 256;      // agents per tile; bounds the per-team pair arrays
 constexpr int kSwQueue = 64;
 
-__host__ __device__ inline size_t sweep_warp_bytes(int T) {
-  size_t b = (size_t)kSwTile * 8 + (size_t)T * (16 + 8 + 4) + (size_t)kSwTile * 4 + 2 * kSwQueue * 4 + kBeBuckets + 16;
+__host__ __device__ inline size_t sweep_smem_bytes(int T, int W) {
+  size_t b = (size_t)kSwTile * 8                 // pairkey
+             + (size_t)T * (16 + 8 + 4)          // egoA, egoB, dist
+             + (size_t)kSwTile * 4               // colfirst
+             + (size_t)W * 2 * kSwQueue * 4      // per-warp near / cp queues
+             + (size_t)W * 2 * 32 * 4            // pooled leftovers
+             + (size_t)W * 16 * 4                // per-warp partial results
+             + (size_t)kSwTile * 2               // BE pair list
+             + 8 * 4 + kBeBuckets + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -42,12 +54,17 @@ struct SweepSmem {
   float2* egoB;                 // [T] (theta, v)
   float* dist;                  // [T] cumulative chord length (BE)
   uint32_t* colfirst;           // [kSwTile] first step with rounded distance 0
-  uint32_t* q_near;             // [kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
-  uint32_t* q_cp;               // [kSwQueue] (agent-in-tile << 8 | step)
+  uint32_t* q_near;             // [W][kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
+  uint32_t* q_cp;               // [W][kSwQueue] (agent-in-tile << 8 | step)
+  uint32_t* pool_near;          // [W * 32] leftovers of all warps
+  uint32_t* pool_cp;            // [W * 32]
+  float* red;                   // [W][16]
+  uint32_t* scal;               // [8]: 0 |min(a, 0)| (float bits), 1 BE list length, 2 pooled near, 3 pooled cp
+  uint16_t* be_list;            // [kSwTile]
   uint8_t* inv;                 // [kBeBuckets + 1]
 };
 
-__device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T) {
+__device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int W) {
   SweepSmem w;
   w.pairkey = reinterpret_cast<unsigned long long*>(base);
   w.egoA = reinterpret_cast<float4*>(w.pairkey + kSwTile);
@@ -55,8 +72,13 @@ __device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T) {
   w.dist = reinterpret_cast<float*>(w.egoB + T);
   w.colfirst = reinterpret_cast<uint32_t*>(w.dist + T);
   w.q_near = w.colfirst + kSwTile;
-  w.q_cp = w.q_near + kSwQueue;
-  w.inv = reinterpret_cast<uint8_t*>(w.q_cp + kSwQueue);
+  w.q_cp = w.q_near + (size_t)W * kSwQueue;
+  w.pool_near = w.q_cp + (size_t)W * kSwQueue;
+  w.pool_cp = w.pool_near + (size_t)W * 32;
+  w.red = reinterpret_cast<float*>(w.pool_cp + (size_t)W * 32);
+  w.scal = reinterpret_cast<uint32_t*>(w.red + (size_t)W * 16);
+  w.be_list = reinterpret_cast<uint16_t*>(w.scal + 8);
+  w.inv = reinterpret_cast<uint8_t*>(w.be_list + kSwTile);
   return w;
 }
 
@@ -98,16 +120,21 @@ __device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, 
   }
 }
 
+struct SweepShape {
+  int lg_agents;   // log2 of the agents held by one warp (0..5); a warp has 32 >> lg_agents time slices
+};
+
 // ---------------------------------------------------------------------------------------------
 template <uint32_t MASK, bool STATS>
-__global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k) {
+__global__ void __launch_bounds__(kSwMaxWarps * 32, 3)
+fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, wib = tid >> 5, W = nthr >> 5;
   const int T = k.T;
-  const SweepSmem w = sweep_smem(smem_raw + (size_t)wib * sweep_warp_bytes(T), T);
-  const int warp0 = blockIdx.x * kSwWarps + wib;
-  const int nwarps = gridDim.x * kSwWarps;
+  const SweepSmem w = sweep_smem(smem_raw, T, W);
+  uint32_t* const q_near = w.q_near + wib * kSwQueue;
+  uint32_t* const q_cp = w.q_cp + wib * kSwQueue;
   const uint32_t mm = MASK ? MASK : k.mmask;
   const bool do_cp = mm & FO_M_CP, do_dce = mm & FO_M_DCE, do_hr = mm & FO_M_HR, do_be = mm & FO_M_BE,
              do_ttc = mm & FO_M_TTC;
@@ -115,23 +142,36 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
   const float rE = sqrtf(k.hEx * k.hEx + k.hEy * k.hEy);   // ego circumradius
   const float cmax = fmaxf(0.0f, fmaxf(k.hc.rs_side, k.hc.rs_rear));
   const int Ap = k.tab.Ap;
+  const BeView bev{w.egoA, w.egoB, w.dist, w.inv};
+  // lane -> (agent within the lane group, time slice); every (warp, slice) owns a contiguous range of steps
+  const int lg = shape.lg_agents;
+  const int group = 1 << lg;                      // agents per warp pass
+  const int la = lane & (group - 1), ls = lane >> lg;
+  const int n_slices = W * (32 >> lg);
+  const int L = (T + n_slices - 1) / n_slices;    // steps per slice
+  const int i_lo = (wib * (32 >> lg) + ls) * L;
+  const int i_hi = min(T, i_lo + L);
   unsigned long long st_dense = 0, st_obb = 0, st_lr = 0, st_cp = 0, st_be = 0, st_probe = 0;
 
-  for (int n = warp0; n < k.N; n += nwarps) {
-    // ---- stage the ego trajectory --------------------------------------------------------------
-    float amin = 0.0f;
+  for (int n = blockIdx.x; n < k.N; n += gridDim.x) {
+    // ---- stage the ego trajectory (whole team) ---------------------------------------------------
     const float* eg = k.ego + (size_t)n * T * 5;
-    __syncwarp();
-    for (int i = lane; i < T; i += 32) {
-      float x = __ldg(eg + i * 5 + 0), y = __ldg(eg + i * 5 + 1), th = __ldg(eg + i * 5 + 2);
-      float v = __ldg(eg + i * 5 + 3);
-      amin = fminf(amin, __ldg(eg + i * 5 + 4));
-      float sn, cs;
-      sincosf(th, &sn, &cs);
-      w.egoA[i] = make_float4(x, y, cs, sn);
-      w.egoB[i] = make_float2(th, v);
+    __syncthreads();                                   // previous trajectory fully consumed
+    if (tid < 8) w.scal[tid] = 0u;
+    __syncthreads();
+    {
+      float amin = 0.0f;
+      for (int i = tid; i < T; i += nthr) {
+        float x = __ldg(eg + i * 5 + 0), y = __ldg(eg + i * 5 + 1), th = __ldg(eg + i * 5 + 2);
+        float v = __ldg(eg + i * 5 + 3);
+        amin = fminf(amin, __ldg(eg + i * 5 + 4));
+        float sn, cs;
+        sincosf(th, &sn, &cs);
+        w.egoA[i] = make_float4(x, y, cs, sn);
+        w.egoB[i] = make_float2(th, v);
+      }
+      if (do_be && amin < 0.0f) atomicMax(&w.scal[0], __float_as_uint(-amin));   // |min(min a, 0)|, be.py:68
     }
-    __syncwarp();
 
     uint32_t rmin = 0xffffffu;                       // warp-uniform running min of round(d * 1000)
     float zb_e = -CUDART_INF_F, zb_o = -CUDART_INF_F; // warp-uniform running maxima of the harm logits
@@ -141,16 +181,13 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
     float btn_all = 0.0f, rcd_all = 0.0f;
     uint32_t flags = 0;
     bool be_ready = false;
-    float be_lo0 = 0.0f;
-
-    const BeView bev{w.egoA, w.egoB, w.dist, w.inv};
 
     for (int a0 = 0; a0 < k.A; a0 += kSwTile) {
       const int nAt = min(kSwTile, k.A - a0);
-      for (int j = lane; j < nAt; j += 32) { w.pairkey[j] = 0ull; w.colfirst[j] = 0xffffffffu; }
-      __syncwarp();
+      for (int j = tid; j < nAt; j += nthr) { w.pairkey[j] = 0ull; w.colfirst[j] = 0xffffffffu; }
+      __syncthreads();                                 // ego staged, pair arrays cleared
       int qn = 0, qc = 0;
-      // per-lane bound state of the current lane tile (refreshed after every drain)
+      // per-lane bound state of the current lane group (refreshed after every drain)
       float lim0 = 0.0f, lim2 = 0.0f, thr2 = CUDART_INF_F;
       float kse = 0.0f, kso = 0.0f, kce = 0.0f, kco = 0.0f;
       bool is_m1 = false;
@@ -175,11 +212,10 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
         thr2 = t2;
       };
 
-      // ---- drains: 32 queued items at a time, all lanes active -------------------------------------------
-      auto drain_near = [&](int cnt) {
+      // ---- drains: up to 32 queued items at a time ------------------------------------------------------
+      auto drain_near = [&](const uint32_t* src, int cnt) {
         uint32_t item = 0;
-        if (lane < cnt) item = w.q_near[qn - cnt + lane];
-        qn -= cnt;
+        if (lane < cnt) item = src[lane];
         __syncwarp();
         uint32_t r = 0xffffffu;
         if (lane < cnt) {
@@ -217,10 +253,9 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
         upd_lim();
         upd_thr();
       };
-      auto drain_cp = [&](int cnt) {
+      auto drain_cp = [&](const uint32_t* src, int cnt) {
         uint32_t item = 0;
-        if (lane < cnt) item = w.q_cp[qc - cnt + lane];
-        qc -= cnt;
+        if (lane < cnt) item = src[lane];
         __syncwarp();
         if (lane < cnt) {
           const int ial = (int)(item >> 8), ii = (int)(item & 0xffu), t = ii - 1;
@@ -254,17 +289,17 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
         __syncwarp();
       };
 
-      // ---- dense sweep: lane tiles of 32 agents x T steps -------------------------------------------------
-      for (int sub = 0; sub < nAt; sub += 32) {
-        const int al = sub + lane;
+      // ---- dense sweep: lane groups of `group` agents x the steps of this lane's slice ------------------
+      for (int sub = 0; sub < nAt; sub += group) {
+        const int al = sub + la;
         const int a = a0 + al;
         const bool alive = al < nAt;
         AgentParams P;
         P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
         if (alive) P = sw_load_params(k.tab.prm + a);
-        const int nS = P.n_states;                        // this agent exists at steps [0, nS)
-        const int nH = min(nS, T - 1);                    // harm is evaluated at steps [0, min(T-1, nS))
-        const int iend = min(T, (int)__reduce_max_sync(kFull, (unsigned)nS));
+        const int nS = min(P.n_states, i_hi);             // this lane evaluates steps [i_lo, nS)
+        const int nH = min(nS, T - 1);                    // harm is evaluated at steps < min(T-1, n_states)
+        const int n_it = (int)__reduce_max_sync(kFull, (unsigned)max(nS - i_lo, 0));
         const bool is_m0 = P.model == 0;
         is_m1 = P.model == 1;
         // harm logit = ks * dv + kc (+ LR4S class coefficient for protected agents)
@@ -272,22 +307,28 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
         kso = (is_m0 ? k.hc.ped_speed : k.hc.rs_speed) * P.ko;
         kce = is_m0 ? k.hc.ia_const : k.hc.rs_const;
         kco = is_m0 ? -k.hc.ped_const : k.hc.rs_const;
-        if (do_hr && alive && P.model == 2 && nH > 0) { acc_ze = CUDART_INF_F; acc_zo = CUDART_INF_F; }
+        if (do_hr && alive && P.model == 2 && nH > i_lo) { acc_ze = CUDART_INF_F; acc_zo = CUDART_INF_F; }
         lim0 = rE + P.pad;
         upd_lim();
         upd_thr();
         const float hlb2 = P.hlb * P.hlb, hlbm2 = -2.0f * P.hlb;
         const uint32_t item0 = (uint32_t)al << 8;
-        const float4* t0 = k.tab.t0 + a0 + sub + lane;     // padded to a multiple of 32 agents: always in bounds
-        const float* tv = k.tab.tv + a0 + sub + lane;
+        // time-major table, agents padded to a multiple of 32: the agent index is always in bounds; rows are only
+        // read for steps the agent has (i < n_states <= t_stride)
+        const float4* t0 = k.tab.t0 + (size_t)i_lo * Ap + (a0 + sub + la);
+        const float* tv = k.tab.tv + (size_t)i_lo * Ap + (a0 + sub + la);
         float pxp = 0.0f, pyp = 0.0f;                      // position at i-1 (collision_probability.py:52)
-        float acc_dv2 = 0.0f;                              // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
-        for (int i = 0; i < iend; ++i, t0 += Ap, tv += Ap) {
-          const float4 EA = w.egoA[i];
-          const float ve = w.egoB[i].y;
-          const float4 s0 = __ldg(t0);
-          const float va = __ldg(tv);
+        if (do_cp && i_lo >= 1 && i_lo < nS) { const float4 sp = __ldg(t0 - Ap); pxp = sp.x; pyp = sp.y; }
+        float acc_dv2 = -1.0f;                             // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
+        int i = i_lo;
+        for (int r = 0; r < n_it; ++r, ++i, t0 += Ap, tv += Ap) {
           const bool live = i < nS;
+          float4 s0 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+          float va = 0.0f;
+          if (live) { s0 = __ldg(t0); va = __ldg(tv); }
+          const int ie = min(i, T - 1);
+          const float4 EA = w.egoA[ie];
+          const float ve = w.egoB[ie].y;
           const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
           bool need_obb = false, need_lr = false, ingate = false;
           if (do_dce) {
@@ -312,22 +353,22 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
           const bool near = need_obb | need_lr;
           unsigned b = __ballot_sync(kFull, near);
           if (b) {
-            if (near) w.q_near[qn + __popc(b & lt_mask)] = item0 | (uint32_t)i | (need_obb ? 0x40000000u : 0u) |
-                                                         (need_lr ? 0x80000000u : 0u);
+            if (near) q_near[qn + __popc(b & lt_mask)] = item0 | (uint32_t)i | (need_obb ? 0x40000000u : 0u) |
+                                                       (need_lr ? 0x80000000u : 0u);
             qn += __popc(b);
             __syncwarp();
-            if (qn >= 32) drain_near(32);
+            if (qn >= 32) { qn -= 32; drain_near(q_near + qn, 32); }
           }
           b = __ballot_sync(kFull, ingate);
           if (b) {
-            if (ingate) w.q_cp[qc + __popc(b & lt_mask)] = item0 | (uint32_t)i;
+            if (ingate) q_cp[qc + __popc(b & lt_mask)] = item0 | (uint32_t)i;
             qc += __popc(b);
             __syncwarp();
-            if (qc >= 32) drain_cp(32);
+            if (qc >= 32) { qc -= 32; drain_cp(q_cp + qc, 32); }
           }
           if (STATS) st_dense += live;
         }
-        if (do_hr && is_m0 && nH > 0) {
+        if (do_hr && is_m0 && acc_dv2 >= 0.0f) {
           const float dvm = acc_dv2 * rsqrtf(fmaxf(acc_dv2, 1e-30f));
           acc_ze = fmaxf(acc_ze, fmaf(kse, dvm, kce));
           acc_zo = fmaxf(acc_zo, fmaf(kso, dvm, kco));
@@ -337,17 +378,33 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
           zb_o = fmaxf(zb_o, warp_max_signed(acc_zo));
         }
       }
-      // ---- flush the queues of this agent tile -------------------------------------------------------------
+      // ---- pool what is left in the per-warp queues across the team and drain it cooperatively --------------
       is_m1 = false;
-      while (qn > 0) drain_near(min(qn, 32));
-      while (qc > 0) drain_cp(min(qc, 32));
-      __syncwarp();
+      if (W == 1) {
+        if (qn > 0) drain_near(q_near, qn);
+        if (qc > 0) drain_cp(q_cp, qc);
+      } else {
+        unsigned base_n = 0, base_c = 0;
+        if (lane == 0) {
+          if (qn > 0) base_n = atomicAdd(&w.scal[2], (unsigned)qn);
+          if (qc > 0) base_c = atomicAdd(&w.scal[3], (unsigned)qc);
+        }
+        base_n = __shfl_sync(kFull, base_n, 0);
+        base_c = __shfl_sync(kFull, base_c, 0);
+        if (lane < qn) w.pool_near[base_n + lane] = q_near[lane];
+        if (lane < qc) w.pool_cp[base_c + lane] = q_cp[lane];
+        __syncthreads();
+        const int tot_n = (int)w.scal[2], tot_c = (int)w.scal[3];
+        for (int c = wib * 32; c < tot_n; c += 32 * W) drain_near(w.pool_near + c, min(32, tot_n - c));
+        for (int c = wib * 32; c < tot_c; c += 32 * W) drain_cp(w.pool_cp + c, min(32, tot_c - c));
+      }
+      __syncthreads();                                 // pairkey / colfirst of the tile complete
+      if (tid == 0) { w.scal[2] = 0u; w.scal[3] = 0u; }
 
-      // ---- tile epilogue: harm_with_cp, wttc, BE --------------------------------------------------------------
-      for (int j0 = 0; j0 < nAt; j0 += 32) {
-        const int j = j0 + lane;
-        const unsigned long long key = (j < nAt) ? w.pairkey[j] : 0ull;
-        const uint32_t cf = (j < nAt) ? w.colfirst[j] : 0xffffffffu;
+      // ---- tile epilogue: harm_with_cp, wttc, BE list -----------------------------------------------------------
+      for (int j = tid; j < nAt; j += nthr) {
+        const unsigned long long key = w.pairkey[j];
+        const uint32_t cf = w.colfirst[j];
         if (key != 0ull) {
           const int t = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
           const int a = a0 + j;
@@ -364,19 +421,22 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
           acc_hwc = fmaxf(acc_hwc, sw_sigmoid(zo));
         }
         if (do_ttc) acc_col = min(acc_col, cf);
-        if (do_be && do_ttc) {
-          unsigned m = __ballot_sync(kFull, cf != 0xffffffffu && cf > 0u);   // be.py:49-50
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int a = a0 + j0 + src;
+        if (do_be && do_ttc && cf != 0xffffffffu && cf > 0u)           // be.py:49-50
+          w.be_list[atomicAdd(&w.scal[1], 1u)] = (uint16_t)j;
+      }
+      if (do_be && do_ttc) {
+        __syncthreads();                               // BE list complete
+        const int n_be = (int)w.scal[1];
+        if (n_be > 0) {
+          if (!be_ready) {
+            if (wib == 0) be_prepare(bev, T, lane);
+            __syncthreads();
+            be_ready = true;
+          }
+          const float be_lo0 = rintf(__uint_as_float(w.scal[0]) * 100.0f) / 100.0f;   // be.py:68
+          for (int q = wib; q < n_be; q += W) {        // bisections dealt round-robin to the warps
+            const int a = a0 + (int)w.be_list[q];
             const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
-            if (!be_ready) {
-              be_prepare(bev, T, lane);
-              float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));
-              be_lo0 = rintf(am * 100.0f) / 100.0f;                          // be.py:68
-              be_ready = true;
-            }
             bool range_err = false;
             unsigned probes = 0;
             const float rcd = be_bisect(k, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane,
@@ -387,39 +447,59 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
             if (STATS && lane == 0) { st_be += 1; st_probe += probes; }
           }
         }
+        __syncthreads();                               // list consumed before the next tile refills it
+        if (tid == 0) w.scal[1] = 0u;
       }
-      __syncwarp();
     }  // agent tiles
 
-    // ---- per-trajectory reduction and threshold mask (metric.py:50-98) ----------------------------------
-    const float er = umaxf(acc_er), orr = umaxf(acc_or), cpm = umaxf(acc_cp), hwc_all = umaxf(acc_hwc);
-    const float ze = warp_max_signed(acc_ze), zo = warp_max_signed(acc_zo);
-    const uint32_t col = __reduce_min_sync(kFull, acc_col);
-    if (lane == 0) {
+    // ---- per-trajectory reduction (warp, then team) and threshold mask (metric.py:50-98) --------------------
+    {
+      const float er = umaxf(acc_er), orr = umaxf(acc_or), cpm = umaxf(acc_cp), hwc = umaxf(acc_hwc);
+      const float ze = warp_max_signed(acc_ze), zo = warp_max_signed(acc_zo);
+      const uint32_t col = __reduce_min_sync(kFull, acc_col);
+      const uint32_t fl = __reduce_or_sync(kFull, flags);
+      if (lane == 0) {
+        float* r = w.red + wib * 16;
+        r[0] = er; r[1] = orr; r[2] = cpm; r[3] = hwc; r[4] = ze; r[5] = zo;
+        r[6] = __uint_as_float(rmin); r[7] = __uint_as_float(col); r[8] = __uint_as_float(fl);
+        r[9] = btn_all; r[10] = rcd_all;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float er = 0.0f, orr = 0.0f, cpm = 0.0f, hwc_all = 0.0f, ze = -CUDART_INF_F, zo = -CUDART_INF_F, btn = 0.0f, rcd = 0.0f;
+      uint32_t rmin_t = 0xffffffu, col = 0xffffffffu, fl = 0u;
+      for (int q = 0; q < W; ++q) {
+        const float* r = w.red + q * 16;
+        er = fmaxf(er, r[0]); orr = fmaxf(orr, r[1]); cpm = fmaxf(cpm, r[2]); hwc_all = fmaxf(hwc_all, r[3]);
+        ze = fmaxf(ze, r[4]); zo = fmaxf(zo, r[5]);
+        rmin_t = min(rmin_t, __float_as_uint(r[6])); col = min(col, __float_as_uint(r[7])); fl |= __float_as_uint(r[8]);
+        btn = fmaxf(btn, r[9]); rcd = fmaxf(rcd, r[10]);
+      }
       const float eh = sw_sigmoid(ze), oh = sw_sigmoid(zo);   // logistic is monotone: max harm = logistic(max logit)
       const bool has_agents = k.A > 0 && mm != 0;
-      const double dce_min = (double)rmin / 1000.0;
+      const double dce_min = (double)rmin_t / 1000.0;
       const bool has_col = col != 0xffffffffu;
       const double wttc = has_col ? rint((double)col * k.dtd * 1000.0) / 1000.0 : (double)CUDART_INF;
       bool ok = true;
       if (has_agents) {
-        if (do_be && (k.tmask & FO_T_BE) && (double)btn_all > k.thr_be) ok = false;
+        if (do_be && (k.tmask & FO_T_BE) && (double)btn > k.thr_be) ok = false;
         if (do_hr && (k.tmask & FO_T_HARM) && (double)hwc_all > k.thr_harm) ok = false;
         if (do_hr && (k.tmask & FO_T_RISK) && (double)orr > k.thr_risk) ok = false;
         if (do_hr && (k.tmask & FO_T_CP) && (double)cpm > k.thr_cp) ok = false;
         if (do_ttc && (k.tmask & FO_T_TTC) && has_col && wttc < k.thr_ttc) ok = false;
-        if (do_dce && (k.tmask & FO_T_DCE) && rmin != 0xffffffu && dce_min < k.thr_dce) ok = false;
-        if (flags & FO_F_BE_RANGE) ok = false;
+        if (do_dce && (k.tmask & FO_T_DCE) && rmin_t != 0xffffffu && dce_min < k.thr_dce) ok = false;
+        if (fl & FO_F_BE_RANGE) ok = false;
       }
       k.valid[n] = ok ? 1 : 0;
-      if (k.flags) k.flags[n] = flags;
+      if (k.flags) k.flags[n] = fl;
       if (k.summary) {
         float* sm = k.summary + (size_t)n * FO_SUMMARY_K;
         sm[0] = er; sm[1] = orr; sm[2] = do_hr ? eh : 0.0f; sm[3] = do_hr ? oh : 0.0f; sm[4] = cpm; sm[5] = hwc_all;
-        sm[6] = (rmin == 0xffffffu || !do_dce) ? CUDART_INF_F : (float)dce_min;
+        sm[6] = (rmin_t == 0xffffffu || !do_dce) ? CUDART_INF_F : (float)dce_min;
         sm[7] = has_col ? (float)wttc : CUDART_INF_F;
-        sm[8] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : btn_all;
-        sm[9] = (flags & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd_all;
+        sm[8] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : btn;
+        sm[9] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd;
       }
     }
   }
@@ -437,23 +517,43 @@ __global__ void __launch_bounds__(kSwWarps * 32, 3) fo_metric_sweep_kernel(const
   }
 }
 
+// Team shape.  lg_agents: a warp holds min(32, next power of two >= A) agents, the remaining lanes are time slices.
+// W: as many warps per trajectory as keeps the whole bundle resident in one wave (the latency of a bundle is its
+// slowest trajectory), as long as every (warp, slice) still owns at least 4 steps.
+static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& shape) {
+  int lg = 0;
+  while ((1 << lg) < k.A && lg < 5) ++lg;
+  shape.lg_agents = lg;
+  const int slices_per_warp = 32 >> lg;
+  const int warp_slots = num_sms * 24;                            // 80 registers per thread -> 24 warps per SM
+  int w = warp_slots / (k.N > 0 ? k.N : 1);
+  const int max_w = k.T / (4 * slices_per_warp);
+  if (w > max_w) w = max_w;
+  if (w > kSwMaxWarps) w = kSwMaxWarps;
+  if (w < 1) w = 1;
+  static const char* forced = getenv("FO_TEAM_WARPS");           // measurement switch
+  if (forced) { int f = atoi(forced); if (f >= 1 && f <= kSwMaxWarps) w = f; }
+  W = w;
+}
+
 template <uint32_t MASK, bool STATS>
 static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st) {
-  const size_t smem = sweep_warp_bytes(k.T) * kSwWarps;
+  int W = 1;
+  SweepShape shape;
+  pick_shape(k, num_sms, W, shape);
+  const size_t smem = sweep_smem_bytes(k.T, W);
   static size_t configured = 0;
-  static int per_sm = 1;
-  if (smem != configured) {
+  if (smem > configured) {
     FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS>,
-                                                              kSwWarps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
     configured = smem;
   }
-  const int ctas_needed = (k.N + kSwWarps - 1) / kSwWarps;
+  int per_sm = 1;
+  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS>, W * 32, smem));
+  if (per_sm < 1) per_sm = 1;
   const int full = num_sms * per_sm;
-  const int grid = ctas_needed < full ? ctas_needed : full;   // persistent: warps stride over trajectories
-  fo_metric_sweep_kernel<MASK, STATS><<<grid, kSwWarps * 32, smem, st>>>(k);
+  const int grid = k.N < full ? k.N : full;       // persistent: teams stride over trajectories
+  fo_metric_sweep_kernel<MASK, STATS><<<grid, W * 32, smem, st>>>(k, shape);
   count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;

@@ -88,7 +88,7 @@ def test_latency_config_parity(cuda_device):
 
 
 def test_summary_kernel_equals_detail_kernel(cuda_device):
-    """The flat summary kernel (bench / planner path) against the detail kernel at a size the CPU
+    """The summary kernel (bench / planner path) against the detail kernel at a size the CPU
     oracle would need minutes for: identical masks/flags/discrete values, floats to 1e-5."""
     case = S.make_case(3000, 300, 51, seed=9)       # > 256 agents: exercises agent tiling
     res_d, _ = parity.run_gpu(case, want_pair=True, want_step=True)
