@@ -255,7 +255,40 @@ def run_ours(args):
     evals_total = N_total * A * (T - 1)
     ms, launches, clocks, kern_ms = timed(step_resident, args.steps, args.warmup, sample_clocks=True, per_step_events=True)
     value = evals_total * args.steps / (ms * 1e-3)
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    e2e_how = "torch: pinned H2D + fo_metric_bundle + all_gather + D2H, CUDA events, max over ranks"
+    if world == 1:
+        # the reference-facing C-ABI call with HOST buffers: fo_metric_bundle_host copies the bundle and the raw
+        # predictions to the device, packs the agent table, runs the kernel, copies valid/summary/flags back and
+        # synchronises -- timed with the host clock around the blocking call
+        import ctypes as C
+        ag = eng.agents
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+        keep = [f32(ag.x), f32(ag.y), f32(ag.yaw), f32(ag.v), f32(ag.var_x), f32(ag.var_y),
+                np.ascontiguousarray(ag.n_states, dtype=np.int32), np.ascontiguousarray(ag.kind, dtype=np.int32),
+                f32(ag.length), f32(ag.width), f32(ag.buf_length), f32(ag.buf_width)]
+        raw = L.FoAgentsRaw()
+        raw.n_agents, raw.t_stride = ag.n_agents, ag.t_stride
+        (raw.x, raw.y, raw.yaw, raw.v, raw.var_x, raw.var_y, raw.n_states, raw.kind, raw.length, raw.width,
+         raw.buf_length, raw.buf_width) = [a.ctypes.data for a in keep]
+        prm = eng._args(ego_dev, out)
+        host_flags = torch.empty(n_local, dtype=torch.int32).pin_memory()
+
+        def step_capi():
+            L.check(L.lib.fo_metric_bundle_host(C.c_void_p(ego_host.data_ptr()), n_local, T, C.byref(raw), C.byref(prm),
+                                                C.c_void_p(host_valid.data_ptr()), C.c_void_p(host_summary.data_ptr()),
+                                                C.c_void_p(host_flags.data_ptr()), None, None), "fo_metric_bundle_host")
+
+        for _ in range(max(1, args.warmup // 2)):
+            step_capi()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_capi()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        assert bool((host_valid.to(dev) == out.valid).all()), "C-ABI host call and device-resident call disagree"
+        e2e_how = "fo_metric_bundle_host (C ABI, pinned host buffers in and out), host wall clock around the blocking call"
+    else:
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     e2e_value = evals_total * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -378,12 +411,95 @@ def run_ours(args):
                        "l2": "inputs (1.02 GB bundle) larger than L2, no flush needed" if N_total * T * 20 > 2.5e8
                              else "inputs smaller than L2 (latency case, resident by design)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * T * 5 * 4) * world,
-                    "d2h_bytes_per_step": int(n_local * (1 + 4 * L.FO_SUMMARY_K)) * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(n_local * (1 + 4 + 4 * L.FO_SUMMARY_K)) * world, "ms_per_step": ms_e2e / args.steps,
+                    "how": e2e_how},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "latency": lat}
+    if not args.no_stages:
+        try:
+            line["stages"] = run_stages(dev)
+        except Exception as e:      # secondary numbers must never cost the headline line
+            line["stages"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_stages(dev):
+    """Secondary numbers of the other two stages of the path and of one whole planning cycle (rank 0 only)."""
+    import random
+    import torch
+    from frenetix_occlusion_b200.visibility import raycast_frames
+    from frenetix_occlusion_b200.prediction import rollout_cv
+    out = {}
+    # ---- stage 1, C-vis: 4096 rays x 512 rectangles per frame over 10 k frames (BASELINE.json configs[4]) ----
+    F, R, O = S.C_VIS["n_frames"], S.C_VIS["n_rays"], S.C_VIS["n_obstacles"]
+    rect = torch.from_numpy(S.obstacle_frames(F, O)).to(dev)
+    flags = torch.ones((F, O), dtype=torch.uint8, device=dev)
+    ego = torch.zeros((F, 3), dtype=torch.float32, device=dev)
+    res = raycast_frames(ego, rect, flags, None, 50.0, 360.0, R, device=dev)
+    for _ in range(3):
+        raycast_frames(ego, rect, flags, None, 50.0, 360.0, R, device=dev, out=res)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        raycast_frames(ego, rect, flags, None, 50.0, 360.0, R, device=dev, out=res)
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    out["visibility"] = {"workload": "C-vis 10000 frames x 4096 rays x 512 rectangles", "kernel_ms": ms,
+                         "frames_per_s": F / (ms * 1e-3), "ray_edge_tests_per_s": F * R * 4 * O / (ms * 1e-3),
+                         "algorithmic_bytes": F * (O * 21 + R * 8 + O), "bound": "fp32 (20 flop per ray x edge test)"}
+    del rect, flags, ego, res
+    # ---- stage 2: constant-velocity rollout of 256 phantom agents x 51 states ----------------------------------
+    rng = np.random.default_rng(5)
+    x0, y0, v, phi = rng.uniform(-50, 50, 256), rng.uniform(-50, 50, 256), rng.uniform(1, 10, 256), rng.uniform(-3, 3, 256)
+    rollout_cv(x0, y0, v, phi, 0.1, 5.0, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        rollout_cv(x0, y0, v, phi, 0.1, 5.0, device=dev)
+    torch.cuda.synchronize()
+    out["rollout_cv"] = {"workload": "256 agents x 51 states, host arrays in, device table out",
+                         "wall_us_per_call": (time.perf_counter() - t0) / 20 * 1e6}
+    # ---- one whole planning cycle on the reference's scenario1 (compact scene fixture) ---------------------------
+    scene = os.path.join(ROOT, "tests", "golden", "scene_scenario1.json")
+    if os.path.exists(scene):
+        from frenetix_occlusion_b200 import replay as RP
+        from frenetix_occlusion_b200.interface import FOInterface
+        from frenetix_occlusion_b200.scenario import scenario_from_dict
+        with open(scene) as f:
+            doc = json.load(f)
+        random.seed(7)
+        sc = scenario_from_dict(doc["scene"])
+        eg = RP.OpenLoopEgo(sc)
+        fo = FOInterface(sc, eg.reference_path, RP.DEFAULT_VEHICLE, sc.dt, config_path=RP.deployment_config(), device=str(dev))
+        t_eval, t_assess, n_sp = [], [], []
+        for ts_ in (0, 6, 12, 18):
+            st = eg.state(ts_)
+            fan = torch.from_numpy(RP.frenet_fan(eg.cosy, st["pos_cl"][0], st["pos_cl"][1], st["v"],
+                                                 speed_factors=np.linspace(0, 1.3, 40), lateral_targets=np.linspace(-1.5, 1.5, 25)
+                                                 ).astype(np.float32)).to(dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fo.evaluate_scenario({}, st["pos"], st["orientation"], st["pos_cl"], st["v"], ts_, eg.cosy)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            r = fo.assess_bundle(fan)
+            nvalid = int(r.valid.sum().item())
+            t2 = time.perf_counter()
+            t_eval.append((t1 - t0) * 1e3)
+            t_assess.append((t2 - t1) * 1e3)
+            n_sp.append((len(fo.spawn_points), len(fo.agent_manager.predictions), nvalid))
+        out["planning_cycle"] = {"workload": "scenario1 (left turn, truck-occluded cyclist), 1000-trajectory fan, default metrics",
+                                 "evaluate_scenario_ms": t_eval, "assess_bundle_ms": t_assess,
+                                 "spawn_points_predictions_valid": n_sp,
+                                 "note": "host wall clock; evaluate_scenario = visibility + spawn locator (host bookkeeping on "
+                                         "GPU-classified samples) + rollouts; assess_bundle = pack + one kernel + read-back"}
+    return out
 
 
 def main():
@@ -395,6 +511,7 @@ def main():
     ap.add_argument("--workload", default="c-sweep", choices=["c-sweep", "c-lat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

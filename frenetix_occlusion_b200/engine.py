@@ -216,6 +216,10 @@ class MetricEngine:
         """[N, T, 5] -> contiguous float32 CUDA tensor (origin-shifted when given as host float64)."""
         if isinstance(ego, torch.Tensor) and ego.is_cuda:
             t = ego
+            if np.any(self.origin != 0.0):
+                # device tensors are in the caller's frame: shift them like the agents (float64 offset vector)
+                off = torch.tensor([self.origin[0], self.origin[1], 0.0, 0.0, 0.0], dtype=torch.float64, device=t.device)
+                t = (t.to(torch.float64) - off).to(torch.float32)
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.to(torch.float32).contiguous()
             return t

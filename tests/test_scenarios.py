@@ -196,3 +196,67 @@ def test_cuda_point_classification_matches_oracle(seed, n_obst, ring, fov, cuda_
     bad = (((gf & VO.PT_SHADOWED) != 0) != ((of & VO.PT_SHADOWED) != 0)) & ~inside
     assert bad.mean() < 2e-3, int(bad.sum())
     assert ((of & VO.PT_VISIBLE) != 0).sum() > 50 and ((of & VO.PT_OCCLUDED) != 0).sum() > 50
+
+
+@pytest.mark.gpu
+def test_interface_edge_cases(cuda_device):
+    """No phantom agents -> ({}, True) and an all-valid bundle (metric.py:44-45); empty point queries; a scenario
+    without obstacles; the per-trajectory plugin protocol on pipeline predictions."""
+    import torch
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.interface import FOInterface
+    from frenetix_occlusion_b200.scenario import scenario_from_dict
+    doc = _load("scene_scenario3.json")
+    scene = dict(doc["scene"])
+    scene["obstacles"] = []
+    sc = scenario_from_dict(scene)
+    ego = R.OpenLoopEgo(sc)
+    cfg = R.deployment_config(agents=None)
+    for key in ("spawn_points_behind_turn", "spawn_point_behind_dynamic_obstacle", "spawn_point_behind_static_obstacle"):
+        cfg["spawn_locator"][key] = False
+    fo = FOInterface(sc, ego.reference_path, R.DEFAULT_VEHICLE, sc.dt, config_path=cfg)
+    st = ego.state(0)
+    area = fo.evaluate_scenario({}, st["pos"], st["orientation"], st["pos_cl"], st["v"], 0, ego.cosy)
+    assert fo.spawn_points == [] and fo.agent_manager.predictions == {}
+    assert area.contains(st["pos"] + np.array([1.0, 0.0])) and not area.is_empty and area.area > 10.0
+    assert fo.sensor_model.visible_objects_timestep == []
+    f, b, lan = fo.sensor_model._classify(np.zeros((0, 2)))
+    assert len(f) == 0 and len(b) == 0 and len(lan) == 0
+    fan = R.frenet_fan(ego.cosy, st["pos_cl"][0], st["pos_cl"][1], st["v"])
+    r = fo.assess_bundle(fan)
+    torch.cuda.synchronize()
+    assert bool(r.valid.all())
+
+    class _T:
+        pass
+    t = _T()
+    t.cartesian = _T()
+    t.cartesian.x, t.cartesian.y, t.cartesian.theta, t.cartesian.v, t.cartesian.a = (fan[5, :, i] for i in range(5))
+    assert fo.trajectory_safety_assessment(t) == ({}, True)
+    # occluded area: a point far behind the ego is on the road but outside the +-90 degree sector
+    back = ego.cosy.convert_to_cartesian_coords(max(st["pos_cl"][0] - 4.0, 0.0), 0.0)
+    assert not fo.sensor_model.occluded_area.contains(back)
+
+
+@pytest.mark.gpu
+def test_device_and_host_bundles_agree(cuda_device):
+    """A CUDA tensor bundle goes through the same origin shift as a host array (regression: device tensors used to be
+    evaluated un-shifted against shifted agents)."""
+    import torch
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.interface import FOInterface
+    from frenetix_occlusion_b200.scenario import scenario_from_dict
+    doc = _load("scene_scenario1.json")
+    random.seed(7)
+    sc = scenario_from_dict(doc["scene"])
+    ego = R.OpenLoopEgo(sc)
+    fo = FOInterface(sc, ego.reference_path, R.DEFAULT_VEHICLE, sc.dt, config_path=R.deployment_config())
+    st = ego.state(0)
+    fo.evaluate_scenario({}, st["pos"], st["orientation"], st["pos_cl"], st["v"], 0, ego.cosy)
+    fan = R.frenet_fan(ego.cosy, st["pos_cl"][0], st["pos_cl"][1], st["v"]).astype(np.float32)
+    r_host = fo.assess_bundle(fan.astype(np.float64))
+    r_dev = fo.assess_bundle(torch.from_numpy(fan).cuda())
+    torch.cuda.synchronize()
+    assert len(fo.agent_manager.predictions) == 3
+    assert torch.equal(r_host.valid, r_dev.valid) and 0 < int(r_host.valid.sum()) < len(fan)
+    assert torch.allclose(r_host.summary, r_dev.summary, rtol=1e-4, atol=1e-6, equal_nan=True)
