@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfo_b200.so")
+LIB_PATH = os.environ.get("FO_LIB_PATH") or os.path.join(_HERE, "libfo_b200.so")   # FO_LIB_PATH: A/B builds
 
 FO_OK = 0
 FO_MAX_STATES = 128

@@ -35,6 +35,13 @@ namespace fo {
 constexpr int kSwMaxWarps = 8;
 constexpr int kSwTile = 256;      // agents per tile; bounds the per-team pair arrays
 constexpr int kSwQueue = 64;
+#ifndef FO_SW_MINB
+#define FO_SW_MINB 4
+#endif
+#ifndef FO_SW_UNROLL
+#define FO_SW_UNROLL 1
+#endif
+constexpr int kSwUnroll = FO_SW_UNROLL;
 
 __host__ __device__ inline size_t sweep_smem_bytes(int T, int W) {
   size_t b = (size_t)kSwTile * 8                 // pairkey
@@ -126,7 +133,7 @@ struct SweepShape {
 
 // ---------------------------------------------------------------------------------------------
 template <uint32_t MASK, bool STATS>
-__global__ void __launch_bounds__(kSwMaxWarps * 32, 3)
+__global__ void __launch_bounds__(kSwMaxWarps * 32, FO_SW_MINB)
 fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -321,6 +328,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (do_cp && i_lo >= 1 && i_lo < nS) { const float4 sp = __ldg(t0 - Ap); pxp = sp.x; pyp = sp.y; }
         float acc_dv2 = -1.0f;                             // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
         int i = i_lo;
+#pragma unroll kSwUnroll
         for (int r = 0; r < n_it; ++r, ++i, t0 += Ap, tv += Ap) {
           const bool live = i < nS;
           float4 s0 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
@@ -380,10 +388,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       }
       // ---- pool what is left in the per-warp queues across the team and drain it cooperatively --------------
       is_m1 = false;
-      if (W == 1) {
-        if (qn > 0) drain_near(q_near, qn);
-        if (qc > 0) drain_cp(q_cp, qc);
-      } else {
+      {
         unsigned base_n = 0, base_c = 0;
         if (lane == 0) {
           if (qn > 0) base_n = atomicAdd(&w.scal[2], (unsigned)qn);
@@ -525,7 +530,7 @@ static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& sh
   while ((1 << lg) < k.A && lg < 5) ++lg;
   shape.lg_agents = lg;
   const int slices_per_warp = 32 >> lg;
-  const int warp_slots = num_sms * 24;                            // 80 registers per thread -> 24 warps per SM
+  const int warp_slots = num_sms * 8 * FO_SW_MINB;               // registers per thread are capped for FO_SW_MINB 256-thread CTAs per SM
   int w = warp_slots / (k.N > 0 ? k.N : 1);
   const int max_w = k.T / (4 * slices_per_warp);
   if (w > max_w) w = max_w;

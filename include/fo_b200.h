@@ -139,7 +139,7 @@ typedef struct FoMetricArgs {
 
 /* Stage 3, the dense core: every trajectory x every phantom prediction x every step.
  * Replaces Metric.evaluate_metrics (metrics/metric.py:35-100) and everything it dispatches to
- * (cp.py, dce.py, ttc.py, ttce.py, wttc.py, hr.py, be.py, metrics/utils/*.py) for a whole bundle. */
+ * (cp.py, dce.py, ttc.py, ttce.py, wttc.py, hr.py, be.py, metrics/utils/ helpers) for a whole bundle. */
 int fo_metric_bundle(const FoMetricArgs *args, void *stream);
 
 /* Work counters of one pass of the summary path over the bundle (same arguments as fo_metric_bundle, pair and
