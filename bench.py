@@ -324,6 +324,17 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same launch shape
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            tr = json.load(f)
+        if wl["name"] == "C-sweep":
+            traffic = int(tr["traffic"] * (n_local / 1_000_000))
+            traffic_src = tr["source"]
+    except Exception:
+        pass
+
     k_ms = float(np.mean(kern_ms)) if kern_ms else ms / args.steps
     evals_local = n_local * A * (T - 1)
     achieved_tflops = evals_local * flop_per_eval / (k_ms * 1e-3) / 1e12
@@ -331,7 +342,7 @@ def run_ours(args):
     roofline = {"bound": "fp32", "kernel": "fo_metric_sweep_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
                 "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "peak_source": peak_src,
                 "kernel_ms": k_ms, "flop_per_eval": flop_per_eval, "gate_fraction": g_frac, "be_pair_fraction": be_pairs,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "executed": {"note": "work the kernel really evaluates after its exact bounds (fo_metric_stats on a "
                                      f"{samp}-trajectory sample): fractions per (traj, agent, step) evaluation",
                              "flop_per_eval": executed_flop_per_eval,
