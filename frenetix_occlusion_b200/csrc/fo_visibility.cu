@@ -14,6 +14,7 @@ namespace fo {
 
 constexpr int kVisThreads = 256;
 constexpr int kVisTile = 1024;   // staged edges per tile: 1024 * (16 + 8) B = 24 KB
+constexpr int kVisTrCap = 512;   // listed transparent obstacles per frame (more: fall back to scanning all flags)
 
 struct VisEdge {
   float4 g;   // a.x, a.y, e.x, e.y   (segment a -> a + e, ego frame)
@@ -55,6 +56,8 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   __shared__ float4 sg[kVisTile];
   __shared__ float2 st[kVisTile];   // (cross(a, e), owner as int bits)
   __shared__ int s_count;
+  __shared__ int s_ntr;                 // transparent (bicycle) obstacles of this frame
+  __shared__ uint16_t s_tr[kVisTrCap];
   const int f = blockIdx.y;
   const int r = blockIdx.x * kVisThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -82,6 +85,20 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   const int n_cand = n_rect_edges + k.n_boundary;
   const float* rect = k.rect + (size_t)f * k.n_obstacles * 5;
   const uint8_t* flags = k.rect_flags + (size_t)f * k.n_obstacles;
+
+  // transparent obstacles (type 'bicycle', sensor_model.py:177) cast no shadow but can be seen: list them once
+  if (threadIdx.x == 0) s_ntr = 0;
+  __syncthreads();
+  if (k.visible) {
+    for (int o = threadIdx.x; o < k.n_obstacles; o += kVisThreads) {
+      const uint8_t fl = flags[o];
+      if ((fl & FO_RECT_EXISTS) && (fl & FO_RECT_TRANSPARENT)) {
+        const int p = atomicAdd(&s_ntr, 1);
+        if (p < kVisTrCap) s_tr[p] = (uint16_t)o;
+      }
+    }
+  }
+  __syncthreads();
 
   for (int base = 0; base < n_cand; base += kVisTile) {
     if (threadIdx.x == 0) s_count = 0;
@@ -154,7 +171,11 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
     if (k.visible) {
       if (owner >= 0) k.visible[(size_t)f * k.n_obstacles + owner] = 1;
       // transparent obstacles (bicycles): visible when the ray crosses them before its first opaque hit
-      for (int o = 0; o < k.n_obstacles; ++o) {
+      const int ntr = s_ntr;
+      const bool listed = ntr <= kVisTrCap && k.n_obstacles <= 65535;
+      const int n_scan = listed ? ntr : k.n_obstacles;
+      for (int q = 0; q < n_scan; ++q) {
+        const int o = listed ? (int)s_tr[q] : q;
         const uint8_t fl = flags[o];
         if ((fl & FO_RECT_EXISTS) && (fl & FO_RECT_TRANSPARENT)) {
           const float cx = rect[o * 5 + 0] - ex0, cy = rect[o * 5 + 1] - ey0;
