@@ -168,3 +168,30 @@ def test_edge_cases(cuda_device):
     sm = r.summary.cpu().numpy()
     assert np.array_equal(sm[:, 6:], res0["summary"][:, 6:], equal_nan=True)       # dce / wttc / BE: discrete
     np.testing.assert_allclose(sm[:, :6], res0["summary"][:, :6], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,n,a,t", [(51, 1, 1, 31), (52, 3, 2, 31), (53, 37, 3, 31), (54, 20, 5, 51), (55, 64, 9, 31),
+                                        (56, 50, 17, 31), (57, 16, 33, 31), (58, 8, 257, 31), (59, 6, 600, 16),
+                                        (60, 5, 40, 128), (61, 1500, 32, 31), (62, 9000, 8, 31)])
+def test_summary_kernel_shapes(seed, n, a, t, cuda_device):
+    """Lane-group boundaries (agents 1..33 -> 1..32 lanes per slice), more than one 256-agent tile, the maximum
+    number of states (FO_MAX_STATES = 128), a single trajectory, and bundles on both sides of the one-wave limit
+    (team width 1..8)."""
+    case = S.make_case(n, a, t, seed=seed)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    _check(parity.compare_bundle(out, res, case))
+
+
+def test_ragged_agent_lengths_summary(cuda_device):
+    """Predictions shorter and longer than the ego horizon (dce.py:87-88, collision_probability.py:49-51,
+    harm_model.py:67-70) through the summary kernel."""
+    case = S.make_case(120, 12, 31, seed=71, agent_states=51)
+    for k, ag in enumerate(case["agents"]):
+        keep = [51, 31, 30, 12, 2, 1][k % 6]
+        for key in ("pos", "yaw", "v", "var"):
+            ag[key] = np.asarray(ag[key])[:keep]
+    out = MO.evaluate_bundle(case)
+    for detail in (False, True):
+        res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
+        _check(parity.compare_bundle(out, res, case))
