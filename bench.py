@@ -489,6 +489,7 @@ def run_stages(dev):
         eg = RP.OpenLoopEgo(sc)
         fo = FOInterface(sc, eg.reference_path, RP.DEFAULT_VEHICLE, sc.dt, config_path=RP.deployment_config(), device=str(dev))
         t_eval, t_assess, n_sp = [], [], []
+        per_traj_us = None
         for ts_ in (0, 6, 12, 18):
             st = eg.state(ts_)
             fan = torch.from_numpy(RP.frenet_fan(eg.cosy, st["pos_cl"][0], st["pos_cl"][1], st["v"],
@@ -502,12 +503,28 @@ def run_stages(dev):
             r = fo.assess_bundle(fan)
             nvalid = int(r.valid.sum().item())
             t2 = time.perf_counter()
+            if ts_ == 6 and fo.agent_manager.predictions:
+                # the reference's per-trajectory protocol: one call per candidate (interface.py:216-219)
+                host_fan = fan[:40].cpu().numpy().astype(np.float64)
+                trajs = []
+                for q in range(len(host_fan)):
+                    tr = type("T", (), {})()
+                    tr.cartesian = type("C", (), {})()
+                    tr.cartesian.x, tr.cartesian.y, tr.cartesian.theta, tr.cartesian.v, tr.cartesian.a = \
+                        (host_fan[q, :, c] for c in range(5))
+                    trajs.append(tr)
+                fo.trajectory_safety_assessment(trajs[0])
+                tq = time.perf_counter()
+                for tr in trajs[1:]:
+                    fo.trajectory_safety_assessment(tr)
+                per_traj_us = (time.perf_counter() - tq) / (len(trajs) - 1) * 1e6
             t_eval.append((t1 - t0) * 1e3)
             t_assess.append((t2 - t1) * 1e3)
             n_sp.append((len(fo.spawn_points), len(fo.agent_manager.predictions), nvalid))
         out["planning_cycle"] = {"workload": "scenario1 (left turn, truck-occluded cyclist), 1000-trajectory fan, default metrics",
                                  "evaluate_scenario_ms": t_eval, "assess_bundle_ms": t_assess,
                                  "spawn_points_predictions_valid": n_sp,
+                                 "trajectory_safety_assessment_us_per_call": per_traj_us,
                                  "note": "host wall clock; evaluate_scenario = visibility + spawn locator (host bookkeeping on "
                                          "GPU-classified samples) + rollouts; assess_bundle = pack + one kernel + read-back"}
     return out

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..engine import AgentSet, MetricEngine
+from ..engine import AgentSet, BundleResult, MetricEngine
 
 _ALL = ["hr", "ttc", "be", "ttce", "dce", "wttc", "cp"]
 
@@ -61,14 +61,27 @@ class MetricCore:
         if key == self._cache_key and self._cache is not None:
             return self._cache
         ego = trajectory_to_array(trajectory)
-        r = self.engine.assess(ego[None], want_pair=True, want_step=True)
-        torch.cuda.current_stream(self.engine.device).synchronize()
         A = self.engine.n_agents
         T = ego.shape[0]
-        d = {"valid": bool(r.valid[0].item()), "flags": int(r.flags[0].item()) & 0xffffffff,
-             "summary": r.summary[0].cpu().numpy().astype(np.float64),
-             "pair": r.pair[0].cpu().numpy().astype(np.float64) if A else np.zeros((0, L.FO_PAIR_K)),
-             "step": r.step[0].cpu().numpy().astype(np.float64) if (A and T > 1) else np.zeros((A, 0, L.FO_STEP_K)),
+        # all outputs of the 1-trajectory launch live in ONE device buffer -> one device-to-host copy
+        n_pair, n_step = A * L.FO_PAIR_K, A * max(T - 1, 0) * L.FO_STEP_K
+        off_flags, off_sum = 16, 32
+        off_pair = off_sum + 4 * ((L.FO_SUMMARY_K + 3) // 4 * 4)
+        off_step = off_pair + 4 * n_pair
+        total = off_step + 4 * n_step
+        dev = self.engine.device
+        buf = torch.empty(max(total, 64), dtype=torch.uint8, device=dev)
+        out = BundleResult(buf[0:1], buf[off_sum:off_sum + 4 * L.FO_SUMMARY_K].view(torch.float32).view(1, L.FO_SUMMARY_K),
+                           buf[off_flags:off_flags + 4].view(torch.int32))
+        out.pair = buf[off_pair:off_pair + 4 * n_pair].view(torch.float32).view(1, A, L.FO_PAIR_K)
+        out.step = buf[off_step:off_step + 4 * n_step].view(torch.float32).view(1, A, max(T - 1, 0), L.FO_STEP_K)
+        self.engine.assess(ego[None], out=out)
+        host = buf.cpu().numpy()          # synchronises the stream
+        f32 = lambda lo, n: host[lo:lo + 4 * n].view(np.float32).astype(np.float64)  # noqa: E731
+        d = {"valid": bool(host[0]), "flags": int(host[off_flags:off_flags + 4].view(np.uint32)[0]),
+             "summary": f32(off_sum, L.FO_SUMMARY_K),
+             "pair": f32(off_pair, n_pair).reshape(A, L.FO_PAIR_K) if A else np.zeros((0, L.FO_PAIR_K)),
+             "step": f32(off_step, n_step).reshape(A, T - 1, L.FO_STEP_K) if (A and T > 1) else np.zeros((A, 0, L.FO_STEP_K)),
              "ids": list(self.engine.agents.ids) if self.engine.agents is not None else [],
              "n_states": self.engine.agents.n_states if self.engine.agents is not None else np.zeros(0, int),
              "T": T}
