@@ -72,7 +72,7 @@ class FoPointQueryArgs(C.Structure):
                 ("ego", C.c_void_p), ("points", C.c_void_p), ("rect", C.c_void_p), ("rect_flags", C.c_void_p),
                 ("boundary", C.c_void_p), ("poly_xy", C.c_void_p), ("poly_off", C.c_void_p),
                 ("sensor_radius", C.c_float), ("sensor_angle_deg", C.c_float), ("occluded_radius", C.c_float),
-                ("focus_obstacle", C.c_int32),
+                ("focus_obstacle", C.c_int32), ("focus_margin", C.c_float),
                 ("flags", C.c_void_p), ("blocker", C.c_void_p), ("lanelets", C.c_void_p)]
 
 
@@ -95,7 +95,7 @@ class FoRolloutPathArgs(C.Structure):
 
 HIT_NONE, HIT_BOUNDARY = -1, -2
 RECT_EXISTS, RECT_TRANSPARENT = 1, 2
-PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW = 1, 2, 4, 8, 16, 32, 64
+PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW, PT_FOCUS_NEAR = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/fo_b200.h declares: name -> (restype, argtypes)
 _PROTOS = {

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kPtThreads) fo_points_kernel(const FoPointQuer
   // ---- shadow test: nearest crossing of the segment origin -> p ---------------------------------------
   float best_num = 2.0f, best_den = 1.0f;   // t = num / den, start above 1
   int owner = FO_HIT_NONE;
-  bool in_obst = false, focus_cross = false, in_focus = false;
+  bool in_obst = false, focus_cross = false, in_focus = false, near_focus = false;
   const int n_rect_edges = k.n_obstacles * 4;
   const int n_cand = n_rect_edges + k.n_boundary;
   for (int base = 0; base < n_cand; base += kPtTile) {
@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(kPtThreads) fo_points_kernel(const FoPointQuer
         float sn, cs;
         sincosf(k.rect[o * 5 + 2], &sn, &cs);
         const float lx = dx * cs + dy * sn, ly = -dx * sn + dy * cs;
+        if (o == k.focus_obstacle) {
+          const float ex = fmaxf(fabsf(lx) - k.rect[o * 5 + 3], 0.0f), ey = fmaxf(fabsf(ly) - k.rect[o * 5 + 4], 0.0f);
+          near_focus = fmaf(ex, ex, ey * ey) <= k.focus_margin * k.focus_margin;
+        }
         if (fabsf(lx) <= k.rect[o * 5 + 3] && fabsf(ly) <= k.rect[o * 5 + 4]) {
           in_obst = true;
           if (o == k.focus_obstacle) in_focus = true;
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(kPtThreads) fo_points_kernel(const FoPointQuer
   if (visible) f |= FO_PT_VISIBLE;
   if (occluded) f |= FO_PT_OCCLUDED;
   if (k.focus_obstacle >= 0 && focus_cross && !in_focus) f |= FO_PT_FOCUS_SHADOW;
+  if (k.focus_obstacle >= 0 && near_focus) f |= FO_PT_FOCUS_NEAR;
   k.flags[m] = f;
   if (k.blocker) k.blocker[m] = owner;
   if (k.lanelets) k.lanelets[m] = lan;

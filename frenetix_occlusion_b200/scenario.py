@@ -128,19 +128,42 @@ class LaneletNetwork:
     def lanelet_polygons(self):
         return [l.polygon_vertices for l in self.lanelets]
 
+    def _stacked(self):
+        """All lanelet rings padded to one [L, V, 2] array (the last vertex repeated: zero-length edges never cross)."""
+        if getattr(self, "_stack", None) is None:
+            vmax = max(len(l.polygon_vertices) for l in self.lanelets)
+            st = np.empty((len(self.lanelets), vmax, 2))
+            for k, l in enumerate(self.lanelets):
+                pv = l.polygon_vertices
+                st[k, :len(pv)] = pv
+                st[k, len(pv):] = pv[-1]
+            # edge k of a ring: vertex k-1 -> vertex k; the padding closes the ring through repeated last vertices
+            self._stack = (np.roll(st, 1, axis=1), st)
+            for k, l in enumerate(self.lanelets):          # closing edge: last real vertex -> first vertex
+                self._stack[0][k, 0] = l.polygon_vertices[-1]
+        return self._stack
+
+    def points_in_lanelets(self, P) -> np.ndarray:
+        """Even-odd membership of points [M,2] in every lanelet polygon at once -> bool [M, L]."""
+        P = np.asarray(P, dtype=np.float64).reshape(-1, 2)
+        a, b = self._stacked()
+        x, y = P[:, 0][:, None, None], P[:, 1][:, None, None]
+        x0, y0, x1, y1 = a[None, ..., 0], a[None, ..., 1], b[None, ..., 0], b[None, ..., 1]
+        cond = (y0 > y) != (y1 > y)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xin = (x1 - x0) * (y - y0) / (y1 - y0) + x0
+        return (np.sum(cond & (x < xin), axis=2) % 2).astype(bool)
+
     def find_lanelet_by_position(self, point_list):
-        out = []
-        for p in point_list:
-            p = np.asarray(p, dtype=np.float64).reshape(1, 2)
-            out.append([l.lanelet_id for l in self.lanelets if _points_in_polygon(p, l.polygon_vertices)[0]])
-        return out
+        inside = self.points_in_lanelets(np.asarray([np.asarray(p, dtype=np.float64).reshape(2) for p in point_list]))
+        return [[self.lanelets[k].lanelet_id for k in np.nonzero(row)[0]] for row in inside]
 
     def points_on_road(self, P):
         P = np.asarray(P, dtype=np.float64).reshape(-1, 2)
-        inside = np.zeros(len(P), dtype=bool)
-        for l in self.lanelets:
-            inside |= _points_in_polygon(P, l.polygon_vertices)
-        return inside
+        out = np.zeros(len(P), dtype=bool)
+        for lo in range(0, len(P), 4096):                  # bounded temporaries
+            out[lo:lo + 4096] = self.points_in_lanelets(P[lo:lo + 4096]).any(1)
+        return out
 
     def road_border_segments(self, piece=1.0, eps=2e-3) -> np.ndarray:
         """Exterior of the union of all lanelet polygons as segments [B,4].  A piece of a lanelet edge

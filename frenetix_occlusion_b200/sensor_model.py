@@ -141,10 +141,10 @@ class SensorModel:
         return res.range[0].cpu().numpy(), res.hit[0].cpu().numpy(), \
             (res.visible[0].cpu().numpy() if O else np.zeros(0, np.uint8))
 
-    def _classify(self, points, focus=-1):
+    def _classify(self, points, focus=-1, focus_margin=0.0):
         if self._frame is None:
             raise RuntimeError("calc_visible_and_occluded_area has not been called yet")
-        return self._frame.classify(points, focus_obstacle=focus)
+        return self._frame.classify(points, focus_obstacle=focus, focus_margin=focus_margin)
 
     # ---- sensor_model.py:41-101 ----------------------------------------------------------------------------
     def calc_visible_and_occluded_area(self, timestep, ego_pos, ego_orientation, obstacles):

@@ -173,7 +173,7 @@ class SpawnLocator:
         """Membership of points in  possible_polygon ∩ (obstacle shadow | occluded area) ∩ disc(12 m) − obstacle.buffer(1)
         (spawn_locator.py:254-275)."""
         k = self.sensor_model._obstacle_index[dyn_obst.cr_obstacle.obstacle_id]
-        flags, _, lan = self.sensor_model._classify(P, focus=k)
+        flags, _, lan = self.sensor_model._classify(P, focus=k, focus_margin=1.0)
         mask_bits = np.uint64(0)
         host_ids = []
         for lid in possible_ids:
@@ -189,7 +189,7 @@ class SpawnLocator:
         want = L.PT_FOCUS_SHADOW if opposite else L.PT_OCCLUDED
         inside &= (flags & want) != 0
         inside &= np.hypot(*(P - dyn_obst.current_pos).T) <= self.buffer_around_vehicle_from_side
-        inside &= hf.point_ring_distance(P, dyn_obst.current_corner_points) > 1.0
+        inside &= (flags & L.PT_FOCUS_NEAR) == 0          # - current_polygon.buffer(1), spawn_locator.py:275
         return inside
 
     def _occluded_region_raster(self, dyn_obst, possible_ids, opposite):
@@ -395,14 +395,29 @@ class SpawnLocator:
         if s_phantom > self.s_threshold or s_phantom < self.ego_cl[0] + 3:
             return
         d_offset = self.phantom_offset_d[ego_intention] + self.offset_ref_path[ego_intention]
-        phantom_pos = np.asarray(self.cosy_cl.convert_to_cartesian_coords(s_phantom, d_offset))
-        guard = 0
-        while self.sensor_model.visible_area.intersects_points(hf.disc_samples(phantom_pos, 0.5)):
-            s_phantom = s_phantom + 0.5
-            phantom_pos = np.asarray(self.cosy_cl.convert_to_cartesian_coords(s_phantom, d_offset))
-            guard += 1
-            if guard > 400:      # the reference would loop until the coordinate system raises
+        # walk s in +0.5 m steps until a 0.5 m disc no longer touches the visible area (spawn_locator.py:552-554);
+        # the candidate discs are classified in batches of 32 steps (one device call each) instead of one by one
+        phantom_pos = None
+        for k0 in range(0, 416, 32):
+            cand = []
+            for k in range(k0, k0 + 32):
+                try:
+                    cand.append(np.asarray(self.cosy_cl.convert_to_cartesian_coords(s_phantom + 0.5 * k, d_offset)))
+                except Exception:
+                    break           # the reference raises out of the coordinate system here
+            if not cand:
                 return
+            discs = np.concatenate([hf.disc_samples(c, 0.5) for c in cand])
+            vis = np.atleast_1d(self.sensor_model.visible_area.contains(discs)).reshape(len(cand), -1).any(1)
+            free = np.nonzero(~vis)[0]
+            if len(free):
+                s_phantom = s_phantom + 0.5 * (k0 + int(free[0]))
+                phantom_pos = cand[int(free[0])]
+                break
+            if len(cand) < 32:
+                return
+        if phantom_pos is None:      # the reference would keep walking until the coordinate system raises
+            return
         others = self.fo_obstacles.visible_obstacle_multipolygon or []
         if any(hf.point_ring_distance(phantom_pos[None], ring)[0] <= 0.5 for ring in others):
             return

@@ -123,7 +123,7 @@ class FrameGeometry:
                               self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg,
                               n_rays, device=self.device)
 
-    def classify(self, points, focus_obstacle: int = -1):
+    def classify(self, points, focus_obstacle: int = -1, focus_margin: float = 0.0):
         """Classify world-frame points [M,2]: returns host arrays (flags uint32, blocker int32, lanelets uint64)."""
         P = np.asarray(points, dtype=np.float64).reshape(-1, 2) - self.origin
         M = len(P)
@@ -145,6 +145,7 @@ class FrameGeometry:
             a.poly_off = self.poly_off_d.data_ptr() if self.n_polygons else None
             a.sensor_radius, a.sensor_angle_deg = self.sensor_radius, self.sensor_angle_deg
             a.occluded_radius, a.focus_obstacle = self.occluded_radius, int(focus_obstacle)
+            a.focus_margin = float(focus_margin)
             a.flags, a.blocker, a.lanelets = flags.data_ptr(), blocker.data_ptr(), lan.data_ptr()
             L.check(L.lib.fo_visibility_points(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                     "fo_visibility_points")

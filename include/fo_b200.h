@@ -209,8 +209,10 @@ enum {
   FO_PT_VISIBLE = 1u << 4,      /* IN_SENSOR & ON_ROAD & !SHADOWED & !IN_OBSTACLE  == within visible_area */
   FO_PT_OCCLUDED = 1u << 5,     /* ON_ROAD & within +-90 deg of the heading & closer than occluded_radius
                                    & !VISIBLE                                       == within occluded_area */
-  FO_PT_FOCUS_SHADOW = 1u << 6  /* behind (not inside) obstacle `focus_obstacle` as seen from the ego
+  FO_PT_FOCUS_SHADOW = 1u << 6, /* behind (not inside) obstacle `focus_obstacle` as seen from the ego
                                                                   == within obstacle_occlusions[id] */
+  FO_PT_FOCUS_NEAR = 1u << 7    /* closer than `focus_margin` to obstacle `focus_obstacle` (0 inside)
+                                   == within current_polygon.buffer(focus_margin), spawn_locator.py:275 */
 };
 
 typedef struct FoPointQueryArgs {
@@ -224,7 +226,8 @@ typedef struct FoPointQueryArgs {
   const int32_t *poly_off;     /* dev [n_polygons + 1] offsets into poly_xy */
   float sensor_radius, sensor_angle_deg;
   float occluded_radius;       /* 1.5 * sensor_radius (sensor_model.py:88) */
-  int32_t focus_obstacle;      /* obstacle index for FO_PT_FOCUS_SHADOW, or -1 */
+  int32_t focus_obstacle;      /* obstacle index for FO_PT_FOCUS_SHADOW / FO_PT_FOCUS_NEAR, or -1 */
+  float focus_margin;          /* buffer distance of FO_PT_FOCUS_NEAR [m] */
   uint32_t *flags;             /* dev [M] FO_PT_* */
   int32_t *blocker;            /* dev [M] first opaque thing the segment ego -> point meets: obstacle index |
                                   FO_HIT_BOUNDARY | FO_HIT_NONE; may be NULL */

@@ -53,12 +53,12 @@ class OracleSensorModel(SM.SensorModel):
                                    self.n_rays)
         return rng, hit, vis
 
-    def _classify(self, points, focus=-1):
+    def _classify(self, points, focus=-1, focus_margin=0.0):
         f = self._frame
         P = np.asarray(points, dtype=np.float64).reshape(-1, 2) - f.origin
         P = P.astype(np.float32).astype(np.float64)
         flags, lan = VO.classify_points(P, np.array([0.0, 0.0, f.heading]), f.rect, f.flags, f.boundary, f.polygons,
-                                        f.radius, f.fov, 1.5 * f.radius, focus=focus)
+                                        f.radius, f.fov, 1.5 * f.radius, focus=focus, focus_margin=focus_margin)
         return flags, np.full(len(P), VO.HIT_NONE, dtype=np.int32), lan
 
 

@@ -249,7 +249,8 @@ def rollout_path(path, x0, y0, v0, dt, horizon, t1=3.0, var0=0.1, var_factor=1.0
 
 
 # ------------------------------------------------------------------------------------------------
-PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW = 1, 2, 4, 8, 16, 32, 64
+PT_IN_SENSOR, PT_ON_ROAD, PT_SHADOWED, PT_IN_OBSTACLE, PT_VISIBLE, PT_OCCLUDED, PT_FOCUS_SHADOW, PT_FOCUS_NEAR = \
+    1, 2, 4, 8, 16, 32, 64, 128
 
 
 def points_in_polygon(P, poly):
@@ -265,7 +266,8 @@ def points_in_polygon(P, poly):
     return (np.sum(cond & (x < xin), axis=1) % 2).astype(bool)
 
 
-def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_deg, occluded_radius, focus=-1):
+def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_deg, occluded_radius, focus=-1,
+                    focus_margin=0.0):
     """Point-wise evaluation of the reference's visible / occluded area construction (float64):
     visible_area = road ∩ sector − border-edge shadow quads − obstacles − obstacle shadows
     (sensor_model.py:103-193), occluded_area = (±90° sector of radius 1.5 R) ∩ road − visible_area
@@ -292,6 +294,7 @@ def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_
     cor = rect_corners(rect)
     in_obst = np.zeros(len(P), dtype=bool)
     focus_shadow = np.zeros(len(P), dtype=bool)
+    focus_near = np.zeros(len(P), dtype=bool)
     for o in range(len(rect)):
         if not (flags[o] & RECT_EXISTS) or (flags[o] & RECT_TRANSPARENT):
             continue
@@ -304,6 +307,11 @@ def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_
         in_obst |= inside
         if o == focus:
             focus_shadow = wedge & ~inside
+            # distance to the rectangle (0 inside) <= margin  ==  within polygon.buffer(margin) (round joins)
+            cs, sn = np.cos(rect[o, 2]), np.sin(rect[o, 2])
+            dl = P - rect[o, :2]
+            lx, ly = dl[:, 0] * cs + dl[:, 1] * sn, -dl[:, 0] * sn + dl[:, 1] * cs
+            focus_near = np.hypot(np.maximum(np.abs(lx) - rect[o, 3], 0), np.maximum(np.abs(ly) - rect[o, 4], 0)) <= focus_margin
     lan = np.zeros(len(P), dtype=np.uint64)
     on_road = np.zeros(len(P), dtype=bool)
     for i, poly in enumerate(polygons):
@@ -314,5 +322,6 @@ def classify_points(P, ego, rect, flags, boundary, polygons, sensor_radius, fov_
     visible = in_sensor & on_road & ~shadow & ~in_obst
     occluded = on_road & ~visible & (np.abs(rel) <= np.pi / 2) & (r <= occluded_radius)
     f = (in_sensor * PT_IN_SENSOR + on_road * PT_ON_ROAD + shadow * PT_SHADOWED + in_obst * PT_IN_OBSTACLE
-         + visible * PT_VISIBLE + occluded * PT_OCCLUDED + focus_shadow * PT_FOCUS_SHADOW).astype(np.uint32)
+         + visible * PT_VISIBLE + occluded * PT_OCCLUDED + focus_shadow * PT_FOCUS_SHADOW
+         + focus_near * PT_FOCUS_NEAR).astype(np.uint32)
     return f, lan

@@ -185,12 +185,14 @@ def test_cuda_point_classification_matches_oracle(seed, n_obst, ring, fov, cuda_
     frame = FrameGeometry(origin, ego[2], rect_w, flags, None if boundary is None else boundary + np.tile(origin, 2),
                           [p + origin for p in polys], 50.0, fov)
     focus = int(np.argmax(flags == 1)) if n_obst else -1
-    gf, gb, gl = frame.classify(P + origin, focus_obstacle=focus)
-    of, ol = VO.classify_points(P, np.array([0.0, 0.0, ego[2]]), rect, flags, boundary, polys, 50.0, fov, 75.0, focus=focus)
+    gf, gb, gl = frame.classify(P + origin, focus_obstacle=focus, focus_margin=1.0)
+    of, ol = VO.classify_points(P, np.array([0.0, 0.0, ego[2]]), rect, flags, boundary, polys, 50.0, fov, 75.0, focus=focus,
+                                focus_margin=1.0)
     assert np.array_equal(gl, ol) or (gl != ol).mean() < 1e-3
     inside = (of & VO.PT_IN_OBSTACLE) != 0
     for bit, name in ((VO.PT_IN_SENSOR, "in_sensor"), (VO.PT_ON_ROAD, "on_road"), (VO.PT_IN_OBSTACLE, "in_obstacle"),
-                      (VO.PT_VISIBLE, "visible"), (VO.PT_OCCLUDED, "occluded"), (VO.PT_FOCUS_SHADOW, "focus_shadow")):
+                      (VO.PT_VISIBLE, "visible"), (VO.PT_OCCLUDED, "occluded"), (VO.PT_FOCUS_SHADOW, "focus_shadow"),
+                      (VO.PT_FOCUS_NEAR, "focus_near")):
         bad = ((gf & bit) != 0) != ((of & bit) != 0)
         assert bad.mean() < 2e-3, (name, int(bad.sum()))          # float32 ties on region borders only
     bad = (((gf & VO.PT_SHADOWED) != 0) != ((of & VO.PT_SHADOWED) != 0)) & ~inside
