@@ -159,7 +159,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -431,7 +431,7 @@ def run_ours(args):
             line["stages"] = run_stages(dev)
         except Exception as e:      # secondary numbers must never cost the headline line
             line["stages"] = {"error": repr(e)}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -530,6 +530,28 @@ def run_stages(dev):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries under us print to the C-level stdout (NCCL's version banner): keep stdout for the ONE JSON line by
+    pointing fd 1 at stderr for the duration of the run and writing the line to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -541,6 +563,7 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
