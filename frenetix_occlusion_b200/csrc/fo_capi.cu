@@ -1,5 +1,6 @@
 // Library plumbing: error string, launch counter, version, FP32 probe, host-buffer entry point.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -34,15 +35,22 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, float seed, 
 }
 
 // per-thread device workspace for the host-buffer entry point
+constexpr int kHostChunksMax = 16;
 struct HostWs {
   void* dev = nullptr;
   size_t bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // compute (+ result copies)
+  cudaStream_t copy = nullptr;          // host -> device copies of the bundle
+  cudaEvent_t ready[kHostChunksMax] = {};
 };
 static thread_local HostWs g_ws;
 
 static int ws_reserve(size_t bytes) {
-  if (!g_ws.stream) FO_CUDA_TRY(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
+  if (!g_ws.stream) {
+    FO_CUDA_TRY(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
+    FO_CUDA_TRY(cudaStreamCreateWithFlags(&g_ws.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunksMax; ++i) FO_CUDA_TRY(cudaEventCreateWithFlags(&g_ws.ready[i], cudaEventDisableTiming));
+  }
   if (bytes <= g_ws.bytes) return FO_OK;
   if (g_ws.dev) FO_CUDA_TRY(cudaFree(g_ws.dev));
   g_ws.dev = nullptr; g_ws.bytes = 0;
@@ -111,7 +119,6 @@ extern "C" int fo_metric_bundle_host(const float* ego_host, int32_t n_traj, int3
   FoAgentsRaw d = *ag;
   const float* hsrc[6] = {ag->x, ag->y, ag->yaw, ag->v, ag->var_x, ag->var_y};
   const float** hdst[6] = {&d.x, &d.y, &d.yaw, &d.v, &d.var_x, &d.var_y};
-  FO_CUDA_TRY(cudaMemcpyAsync(d_ego, ego_host, N * T * 5 * 4, cudaMemcpyHostToDevice, st));
   for (int i = 0; i < 6; ++i) {
     float* dp = (float*)take(b_f);
     if (A * Tp) {
@@ -144,11 +151,48 @@ extern "C" int fo_metric_bundle_host(const float* ego_host, int32_t n_traj, int3
     rc = fo_agents_pack(&d, &m.vehicle, d_tab, b_tab, st);
     if (rc != FO_OK) return rc;
   }
-  rc = fo_metric_bundle(&m, st);
-  if (rc != FO_OK) return rc;
-  FO_CUDA_TRY(cudaMemcpyAsync(out_valid, m.valid, N, cudaMemcpyDeviceToHost, st));
-  if (out_summary) FO_CUDA_TRY(cudaMemcpyAsync(out_summary, m.summary, N * FO_SUMMARY_K * 4, cudaMemcpyDeviceToHost, st));
-  if (out_flags) FO_CUDA_TRY(cudaMemcpyAsync(out_flags, m.flags, N * 4, cudaMemcpyDeviceToHost, st));
+  // Large bundles are pipelined: the trajectory range is cut into chunks, chunk k+1 crosses PCIe on the copy stream
+  // while chunk k is evaluated (trajectories are independent), results follow each chunk back on the compute stream.
+  // The first chunk is small (its copy cannot be hidden), every following one four times larger: copying is several
+  // times faster than evaluating, and every launch costs a tail of about one trajectory time per warp.
+  const size_t traj_bytes = T * 5 * 4;
+  static const char* chunk_env = getenv("FO_HOST_CHUNK_MB");           // measurement switch: size of the first chunk
+  const size_t first_bytes = (size_t)(chunk_env && atoi(chunk_env) > 0 ? atoi(chunk_env) : 16) << 20;
+  size_t bound[fo::kHostChunksMax + 1];
+  int chunks = 1;
+  bound[0] = 0; bound[1] = N;
+  if (N * traj_bytes >= 2 * first_bytes && !m.pair && !m.step && traj_bytes > 0) {
+    size_t step = (first_bytes + traj_bytes - 1) / traj_bytes, at = 0;
+    chunks = 0;
+    while (at < N && chunks < fo::kHostChunksMax - 1) {
+      at = (at + step < N) ? at + step : N;
+      bound[++chunks] = at;
+      step *= 4;
+    }
+    if (at < N) bound[++chunks] = N;
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const size_t lo = bound[c], hi = bound[c + 1], n = hi - lo;
+    if (n == 0) continue;
+    FO_CUDA_TRY(cudaMemcpyAsync(d_ego + lo * T * 5, ego_host + lo * T * 5, n * traj_bytes, cudaMemcpyHostToDevice,
+                                fo::g_ws.copy));
+    FO_CUDA_TRY(cudaEventRecord(fo::g_ws.ready[c], fo::g_ws.copy));
+    FO_CUDA_TRY(cudaStreamWaitEvent(st, fo::g_ws.ready[c], 0));
+    FoMetricArgs mc = m;
+    mc.ego = d_ego + lo * T * 5;
+    mc.n_traj = (int32_t)n;
+    mc.valid = m.valid + lo;
+    mc.summary = m.summary + lo * FO_SUMMARY_K;
+    mc.flags = m.flags + lo;
+    if (m.pair) mc.pair = m.pair + lo * A * FO_PAIR_K;
+    if (m.step) mc.step = m.step + lo * A * (T - 1) * FO_STEP_K;
+    rc = fo_metric_bundle(&mc, st);
+    if (rc != FO_OK) return rc;
+    FO_CUDA_TRY(cudaMemcpyAsync(out_valid + lo, mc.valid, n, cudaMemcpyDeviceToHost, st));
+    if (out_summary)
+      FO_CUDA_TRY(cudaMemcpyAsync(out_summary + lo * FO_SUMMARY_K, mc.summary, n * FO_SUMMARY_K * 4, cudaMemcpyDeviceToHost, st));
+    if (out_flags) FO_CUDA_TRY(cudaMemcpyAsync(out_flags + lo, mc.flags, n * 4, cudaMemcpyDeviceToHost, st));
+  }
   if (m.pair) FO_CUDA_TRY(cudaMemcpyAsync(out_pair, m.pair, N * A * FO_PAIR_K * 4, cudaMemcpyDeviceToHost, st));
   if (m.step) FO_CUDA_TRY(cudaMemcpyAsync(out_step, m.step, N * A * (T - 1) * FO_STEP_K * 4, cudaMemcpyDeviceToHost, st));
   FO_CUDA_TRY(cudaStreamSynchronize(st));

@@ -195,3 +195,44 @@ def test_ragged_agent_lengths_summary(cuda_device):
     for detail in (False, True):
         res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
         _check(parity.compare_bundle(out, res, case))
+
+
+@pytest.mark.parametrize("n,a,t,detail", [(200, 12, 31, True), (60000, 4, 31, False), (7, 0, 31, False)])
+def test_host_buffer_entry_point(n, a, t, detail, cuda_device):
+    """fo_metric_bundle_host (the C-ABI call a non-torch embedder makes: host pointers in, host pointers out) equals
+    the device-resident path -- small bundle with detail outputs, a bundle large enough for the chunked H2D/compute
+    pipeline, and no agents."""
+    import ctypes as C
+    import torch
+    from frenetix_occlusion_b200 import _lib as L
+    from frenetix_occlusion_b200.engine import AgentSet, BundleResult, MetricEngine
+    case = S.make_case(n, a, t, seed=81)
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"])
+    ag = AgentSet.from_case(case["agents"])
+    eng.set_agents(ag)
+    ego = np.ascontiguousarray(case["ego"], dtype=np.float32)
+    r = eng.assess(torch.from_numpy(ego).cuda(), want_pair=detail, want_step=detail)
+    torch.cuda.synchronize()
+    f32 = lambda x: np.ascontiguousarray(x, dtype=np.float32)  # noqa: E731
+    keep = [f32(ag.x), f32(ag.y), f32(ag.yaw), f32(ag.v), f32(ag.var_x), f32(ag.var_y),
+            np.ascontiguousarray(ag.n_states, dtype=np.int32), np.ascontiguousarray(ag.kind, dtype=np.int32),
+            f32(ag.length), f32(ag.width), f32(ag.buf_length), f32(ag.buf_width)]
+    raw = L.FoAgentsRaw()
+    raw.n_agents, raw.t_stride = ag.n_agents, max(ag.t_stride, 0)
+    (raw.x, raw.y, raw.yaw, raw.v, raw.var_x, raw.var_y, raw.n_states, raw.kind, raw.length, raw.width, raw.buf_length,
+     raw.buf_width) = [x.ctypes.data if x.size else None for x in keep]
+    out = BundleResult(torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty((n, L.FO_SUMMARY_K), device="cuda"),
+                       torch.empty(n, dtype=torch.int32, device="cuda"))
+    prm = eng._args(torch.from_numpy(ego).cuda(), out)
+    valid, summ, flags = np.empty(n, np.uint8), np.empty((n, L.FO_SUMMARY_K), np.float32), np.empty(n, np.uint32)
+    pair = np.empty((n, a, L.FO_PAIR_K), np.float32) if detail else None
+    step = np.empty((n, a, t - 1, L.FO_STEP_K), np.float32) if detail else None
+    ptr = lambda x: None if x is None else C.c_void_p(x.ctypes.data)  # noqa: E731
+    L.check(L.lib.fo_metric_bundle_host(ptr(ego), n, t, C.byref(raw), C.byref(prm), ptr(valid), ptr(summ), ptr(flags),
+                                        ptr(pair), ptr(step)), "fo_metric_bundle_host")
+    assert np.array_equal(valid, r.valid.cpu().numpy())
+    assert np.array_equal(flags, r.flags.cpu().numpy().astype(np.uint32))
+    assert np.array_equal(summ, r.summary.cpu().numpy(), equal_nan=True)
+    if detail:
+        assert np.array_equal(pair, r.pair.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(step, r.step.cpu().numpy(), equal_nan=True)
