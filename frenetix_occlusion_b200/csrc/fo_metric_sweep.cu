@@ -132,7 +132,9 @@ struct SweepShape {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <uint32_t MASK, bool STATS>
+// UNI: one warp per trajectory and 32 agents per warp pass (the throughput shape): the step index is warp-uniform, so the
+// table rows and the ego state need no per-lane clamping or predication.
+template <uint32_t MASK, bool STATS, bool UNI>
 __global__ void __launch_bounds__(kSwMaxWarps * 32, FO_SW_MINB)
 fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -333,8 +335,9 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           const bool live = i < nS;
           float4 s0 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
           float va = 0.0f;
-          if (live) { s0 = __ldg(t0); va = __ldg(tv); }
-          const int ie = min(i, T - 1);
+          if (UNI) { s0 = __ldg(t0); va = __ldg(tv); }      // i < max n_states <= t_stride: the row exists (padding zeroed)
+          else if (live) { s0 = __ldg(t0); va = __ldg(tv); }
+          const int ie = UNI ? i : min(i, T - 1);
           const float4 EA = w.egoA[ie];
           const float ve = w.egoB[ie].y;
           const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
@@ -541,24 +544,33 @@ static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& sh
   W = w;
 }
 
+template <uint32_t MASK, bool STATS, bool UNI>
+static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st);
+
 template <uint32_t MASK, bool STATS>
 static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st) {
   int W = 1;
   SweepShape shape;
   pick_shape(k, num_sms, W, shape);
+  if (W == 1 && shape.lg_agents == 5) return launch_sweep_shape<MASK, STATS, true>(k, num_sms, W, shape, st);
+  return launch_sweep_shape<MASK, STATS, false>(k, num_sms, W, shape, st);
+}
+
+template <uint32_t MASK, bool STATS, bool UNI>
+static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st) {
   const size_t smem = sweep_smem_bytes(k.T, W);
   static size_t configured = 0;
   if (smem > configured) {
-    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     configured = smem;
   }
   int per_sm = 1;
-  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS>, W * 32, smem));
+  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS, UNI>, W * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const int full = num_sms * per_sm;
   const int grid = k.N < full ? k.N : full;       // persistent: teams stride over trajectories
-  fo_metric_sweep_kernel<MASK, STATS><<<grid, W * 32, smem, st>>>(k, shape);
+  fo_metric_sweep_kernel<MASK, STATS, UNI><<<grid, W * 32, smem, st>>>(k, shape);
   count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;
