@@ -228,8 +228,10 @@ class MetricEngine:
             arr = arr[None]
         arr[..., 0] -= self.origin[0]
         arr[..., 1] -= self.origin[1]
-        host = torch.from_numpy(arr.astype(np.float32)).pin_memory()
-        return host.to(self.device, non_blocking=True)
+        host = torch.from_numpy(arr.astype(np.float32))
+        if host.numel() >= (1 << 18):          # page-locking only pays for bundles of a megabyte and more
+            return host.pin_memory().to(self.device, non_blocking=True)
+        return host.to(self.device)
 
     def _args(self, t, out):
         N, T = int(t.shape[0]), int(t.shape[1])
