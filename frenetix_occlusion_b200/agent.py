@@ -91,13 +91,36 @@ class OAPAgent:
                 "cov_list": np.array([[[v, 0.0], [0.0, v]] for v in var])}
 
     def add_to_commonroad_scenario(self, timestep=0):
-        """agent.py:225-252: the agent becomes a dynamic obstacle whose trajectory starts at timestep + 1."""
+        """agent.py:225-252: the agent becomes a dynamic obstacle whose trajectory starts at timestep + 1.  With
+        commonroad-io installed (the planner's environment) real commonroad objects are built, exactly as the
+        reference does; otherwise the light stand-ins of ``scenario.py`` (replay harness)."""
         pred = self._full_prediction
-        init = State(position=self.initial_state.position, orientation=self.initial_state.orientation,
-                     velocity=self.initial_state.velocity, time_step=timestep)
-        states = [State(position=pred["pos_list"][i], orientation=pred["orientation_list"][i],
-                        velocity=pred["v_list"][i], time_step=timestep + i) for i in range(1, len(pred["pos_list"]))]
-        self.commonroad_dynamic_obstacle = Obstacle(self.agent_id, self.agent_type.lower(), "dynamic", self.shape, init, states)
+        n = len(pred["pos_list"])
+        try:
+            if not type(self.cr_scenario).__module__.startswith("commonroad"):
+                raise ImportError("scenario is not a commonroad-io object")
+            from commonroad.geometry.shape import Rectangle as CRRectangle
+            from commonroad.prediction.prediction import TrajectoryPrediction
+            from commonroad.scenario.obstacle import DynamicObstacle, ObstacleType
+            from commonroad.scenario.state import CustomState, InitialState
+            from commonroad.scenario.trajectory import Trajectory
+        except ImportError:
+            init = State(position=self.initial_state.position, orientation=self.initial_state.orientation,
+                         velocity=self.initial_state.velocity, time_step=timestep)
+            states = [State(position=pred["pos_list"][i], orientation=pred["orientation_list"][i],
+                            velocity=pred["v_list"][i], time_step=timestep + i) for i in range(1, n)]
+            self.commonroad_dynamic_obstacle = Obstacle(self.agent_id, self.agent_type.lower(), "dynamic", self.shape, init,
+                                                        states)
+        else:
+            shape = CRRectangle(self.shape.length, self.shape.width, center=np.array([0.0, 0.0]), orientation=0.0)
+            init = InitialState(position=np.asarray(self.initial_state.position), orientation=self.initial_state.orientation,
+                                velocity=self.initial_state.velocity, time_step=timestep)
+            states = [CustomState(position=np.asarray(pred["pos_list"][i]), orientation=float(pred["orientation_list"][i]),
+                                  velocity=float(pred["v_list"][i]), time_step=timestep + i) for i in range(1, n)]
+            trajectory = Trajectory(initial_time_step=timestep + 1, state_list=states)
+            self.commonroad_dynamic_obstacle = DynamicObstacle(
+                obstacle_id=self.agent_id, obstacle_type=ObstacleType(self.agent_type.lower()), obstacle_shape=shape,
+                initial_state=init, prediction=TrajectoryPrediction(trajectory=trajectory, shape=shape))
         self.cr_scenario.add_objects(self.commonroad_dynamic_obstacle)
 
 
