@@ -61,3 +61,28 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert all(0 <= hi - lo <= (n + w - 1) // w for lo, hi in spans)
+
+
+def test_bundle_packer_round_trip():
+    import types
+    import numpy as np
+    from frenetix_occlusion_b200.adapter import BundlePacker, bundle_from_trajectories
+    rng = np.random.default_rng(0)
+    trajs = []
+    for _ in range(7):
+        c = types.SimpleNamespace(**{f: rng.normal(size=31) for f in ("x", "y", "theta", "v", "a")})
+        trajs.append(types.SimpleNamespace(cartesian=c))
+    ref = bundle_from_trajectories(trajs)
+    assert ref.shape == (7, 31, 5) and np.array_equal(ref[3, :, 2], trajs[3].cartesian.theta)
+    pk = BundlePacker(16, 31, pin=False)
+    got = pk.pack(trajs, origin=(1.5, -2.0)).numpy()
+    assert got.shape == (7, 31, 5) and got.dtype == np.float32
+    exp = ref.copy()
+    exp[..., 0] -= 1.5
+    exp[..., 1] += 2.0
+    assert np.array_equal(got, exp.astype(np.float32))
+    cols = pk.pack_columns(ref[..., 0], ref[..., 1], ref[..., 2], ref[..., 3], ref[..., 4]).numpy()
+    assert np.array_equal(cols, ref.astype(np.float32))
+    import pytest
+    with pytest.raises(ValueError):
+        pk.pack(trajs * 3)
