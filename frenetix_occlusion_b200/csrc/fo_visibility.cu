@@ -139,9 +139,13 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
       pos = __shfl_sync(0xffffffffu, pos, 0);
       if (keep) {
         const int w = pos + __popc(m & ((1u << lane) - 1u));
-        const float exx = bx - ax, eyy = by - ay;
+        float exx = bx - ax, eyy = by - ay;
+        float tn = ax * eyy - ay * exx;                      // cross(a, e)
+        if (tn < 0.0f) {                                     // orient the edge so that cross(a, e) >= 0: a hit then
+          ax = bx; ay = by; exx = -exx; eyy = -eyy; tn = -tn;  // needs cross(d, e) > 0 and the ray test loses its
+        }                                                    // sign products and absolute values
         sg[w] = make_float4(ax, ay, exx, eyy);
-        st[w] = make_float2(ax * eyy - ay * exx, __int_as_float(own));
+        st[w] = make_float2(tn, __int_as_float(own));
       }
     }
     __syncthreads();
@@ -154,10 +158,10 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
         const float2 t = st[j];
         const float D = c * g.w - s * g.z;           // cross(d, e)
         const float un = g.x * s - g.y * c;          // cross(a, d)
-        // t = tn / D >= 0, u = un / D in [0, 1], t < best   (division-free, strict improvement only)
-        const bool okk = (t.x * D >= 0.0f) & (un * D >= 0.0f) & (fabsf(un) <= fabsf(D)) & (fabsf(t.x) < best * fabsf(D));
+        // t = tn / D >= 0 with tn >= 0, u = un / D in [0, 1], t < best   (division-free, strict improvement only)
+        const bool okk = (D > 0.0f) & (un >= 0.0f) & (un <= D) & (t.x < best * D);
         if (okk) {
-          best = fabsf(t.x) / fabsf(D);
+          best = t.x / D;
           owner = __float_as_int(t.y);
         }
       }
