@@ -1,7 +1,7 @@
 // Dense metric core of the Frenetix-Occlusion assessment path, sm_100a -- DETAIL kernel.
 //
 // Used when the caller wants the per-pair / per-step arrays of the reference result dict
-// (drop-in Metric.evaluate_metrics); the throughput path is fo_metric_flat.cu.
+// (drop-in Metric.evaluate_metrics); the throughput / latency path is fo_metric_sweep.cu.
 //
 // One warp owns one ego trajectory; lane = time index (T = 31 fits one warp, longer horizons run
 // NP = ceil(T/32) register passes); the warp loops over all phantom predictions.  Per

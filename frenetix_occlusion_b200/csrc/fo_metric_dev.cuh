@@ -1,5 +1,5 @@
 // Device-side helpers shared by the metric kernels (detail kernel: fo_metric_detail.cu,
-// summary kernel: fo_metric_flat.cu).
+// summary kernel: fo_metric_sweep.cu).
 #pragma once
 #include <math_constants.h>
 

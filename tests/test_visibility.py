@@ -159,3 +159,37 @@ def test_cuda_path_rollout_matches_oracle(cuda_device):
             assert int(g["sample"][j]) == o["sample"], (j, int(g["sample"][j]), o["sample"])
             for key in ("x", "y", "yaw", "v", "var"):
                 np.testing.assert_allclose(g[key][j].cpu().numpy(), o[key], rtol=2e-6, atol=2e-5, err_msg=f"{key} job {j}")
+
+
+@pytest.mark.gpu
+def test_full_size_visibility_sweep_properties(cuda_device):
+    """BASELINE.json configs[4] at FULL size (10,000 frames x 4096 rays x 512 rectangles): frame-sharding and
+    obstacle-order invariance of the ray cast, and two frames against the float64 oracle."""
+    import torch
+    from frenetix_occlusion_b200.visibility import raycast_frames
+    F, R, O = S.C_VIS["n_frames"], S.C_VIS["n_rays"], S.C_VIS["n_obstacles"]
+    rect = torch.from_numpy(S.obstacle_frames(F, O)).cuda()
+    flags = torch.ones((F, O), dtype=torch.uint8, device="cuda")
+    ego = torch.zeros((F, 3), dtype=torch.float32, device="cuda")
+    ego[:, 2] = torch.linspace(-3.0, 3.0, F, device="cuda")
+    whole = raycast_frames(ego, rect, flags, None, 50.0, 360.0, R)
+    torch.cuda.synchronize()
+    h = F // 2
+    a = raycast_frames(ego[:h], rect[:h], flags[:h], None, 50.0, 360.0, R)
+    b = raycast_frames(ego[h:], rect[h:], flags[h:], None, 50.0, 360.0, R)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat((a.range, b.range)).view(torch.int32), whole.range.view(torch.int32))
+    assert torch.equal(torch.cat((a.hit, b.hit)), whole.hit) and torch.equal(torch.cat((a.visible, b.visible)), whole.visible)
+    perm = torch.randperm(O, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    p = raycast_frames(ego, rect[:, perm].contiguous(), flags[:, perm].contiguous(), None, 50.0, 360.0, R)
+    torch.cuda.synchronize()
+    assert torch.equal(p.range.view(torch.int32), whole.range.view(torch.int32))          # first-hit distance: a min
+    assert torch.equal(p.visible, whole.visible[:, perm])
+    mapped = torch.where(p.hit >= 0, perm[p.hit.clamp(min=0).long()].to(torch.int32), p.hit)
+    assert (mapped != whole.hit).float().mean().item() < 1e-4       # equal-distance corner hits may pick the other owner
+    for f in (0, F - 1):
+        o_rng, o_hit, o_vis = VO.raycast(ego[f].cpu().numpy().astype(np.float64), rect[f].cpu().numpy().astype(np.float64),
+                                         np.ones(O, np.uint8), None, 50.0, 360.0, R)
+        g = whole.range[f].cpu().numpy()
+        assert (~np.isclose(g, o_rng, rtol=2e-5, atol=2e-4)).mean() < 0.004
+        assert (whole.hit[f].cpu().numpy() != o_hit).mean() < 0.006
