@@ -1,0 +1,39 @@
+"""Randomised CUDA-vs-oracle campaign: many seeded bundles, both kernels (detail and summary), aggregated tie
+statistics and hard failures.  Run on the GPU box; prints one JSON object (committed under profiles/)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+from frenetix_occlusion_b200 import synthetic as S  # noqa: E402
+from oracle import metric_oracle as MO  # noqa: E402
+import parity  # noqa: E402
+
+rng = np.random.default_rng(2024)
+shapes = [(400, 32, 31), (150, 64, 51), (600, 6, 31), (80, 256, 51), (250, 20, 31), (1000, 3, 31)]
+agg = {"cases": 0, "pairs": 0, "trajectories": 0, "evaluations": 0, "hard_failures": [], "mask_mismatch": 0,
+       "ties_detail": {}, "ties_summary": {}, "cp_max_rel": 0.0}
+for rep_i in range(4):
+    for (n, a, t) in shapes:
+        seed = int(rng.integers(1, 1 << 30))
+        case = S.make_case(n, a, t, seed=seed)
+        out = MO.evaluate_bundle(case)
+        for detail, key in ((True, "ties_detail"), (False, "ties_summary")):
+            res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
+            rep = parity.compare_bundle(out, res, case)
+            for k, v in rep["ties"].items():
+                agg[key][k] = agg[key].get(k, 0) + v
+            agg["mask_mismatch"] += rep.get("mask_mismatch", 0)
+            agg["cp_max_rel"] = max(agg["cp_max_rel"], rep.get("cp_max_rel", 0.0))
+            if rep["fail"]:
+                agg["hard_failures"].append({"seed": seed, "shape": [n, a, t], "detail": detail, "fail": rep["fail"][:3]})
+        agg["cases"] += 1
+        agg["pairs"] += n * a
+        agg["trajectories"] += n
+        agg["evaluations"] += n * a * (t - 1)
+print(json.dumps(agg, indent=1))
