@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
       const int nH = min(T - 1, P.n_states);   // harm range (harm_model.py:67)
       float cp[NP], he[NP], ho[NP];
       uint32_t key[NP];
+      bool tie[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         const int i = lane + 32 * p;
@@ -157,12 +158,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
 
         // ---- DCE: oriented-box distance, axle-shifted ego centre, unbuffered agent shape ----
         key[p] = 0xffffffffu;
+        tie[p] = false;
         if (do_dce && i < nA) {
           float dx = dxr - k.wb * E.c, dy = dyr - k.wb * E.s;
           float rx = fmaf(dx, E.c, dy * E.s), ry = fmaf(dy, E.c, -dx * E.s);
           float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, P.hl, P.hw));
           uint32_t r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);  // np.round(d, 3), dce.py:79
           key[p] = (r << 8) | (uint32_t)i;
+          tie[p] = near_rounding_boundary(d);
         }
 
         // ---- harm at state t = i (same index both sides), harm_model.py:81-105 ----------------
@@ -208,6 +211,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
               }
             }
             cp[p] = prob * (1.0f / 3.0f);
+          }
+        }
+      }
+
+      // ---- rounding ties: candidates for the pair's minimum that sit next to a x.xxx5 boundary are re-rounded from a
+      //      float64 evaluation (a float32 value is off by at most one unit there, hence the margin of two) ----------
+      if (do_dce) {
+        uint32_t kpre = 0xffffffffu;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) kpre = min(kpre, key[p]);
+        kpre = __reduce_min_sync(kFull, kpre);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int i = lane + 32 * p;
+          if (tie[p] && (key[p] >> 8) <= (kpre >> 8) + 2u) {
+            const float4 s0 = __ldg(&k.tab.s0[(size_t)a * k.Tp + i]);
+            const float yaw = __ldg(&k.tab.s1[(size_t)a * k.Tp + i]).x;
+            const uint32_t r = obb_round_mm_f64(e[p].x, e[p].y, e[p].th, k.wb, k.hEx, k.hEy, s0.x, s0.y, yaw, P.hl, P.hw);
+            key[p] = (r << 8) | (uint32_t)i;
           }
         }
       }

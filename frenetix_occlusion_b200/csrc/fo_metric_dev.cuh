@@ -68,6 +68,51 @@ __device__ __forceinline__ float obb_d2(float rx, float ry, float c, float s, fl
   return d2;
 }
 
+// ---- rounding-tie refinement of np.round(d, 3) (dce.py:79) ---------------------------------------------------------
+// The float32 distance carries an error of a few 1e-5 m; when d * 1000 lies within kTieBand of a rounding boundary
+// (x.5) the float64 reference may round the other way.  Such candidates are re-evaluated here in double from the
+// same float32 inputs (the formulation of oracle/geometry.py: SAT, then the 8 corner-to-box distances), so dce,
+// time_dce and the first-collision step agree with the float64 reference except when the exact distance itself sits
+// within 1e-12 of a boundary.  Rare path (a few per cent of the exact distance evaluations), kept out of line.
+constexpr float kTieBand = 0.08f;
+
+__device__ __forceinline__ bool near_rounding_boundary(float d) {
+  const float t = d * 1000.0f;
+  return fabsf(t - floorf(t) - 0.5f) < kTieBand;
+}
+
+__device__ __forceinline__ double pt_box_d2_f64(double px, double py, double hx, double hy) {
+  const double dx = fmax(fabs(px) - hx, 0.0), dy = fmax(fabs(py) - hy, 0.0);
+  return dx * dx + dy * dy;
+}
+
+// ego reference point (ex, ey, eth), rectangle centre wb ahead; agent rectangle (ax, ay, ayaw); returns round(d * 1000)
+static __device__ __noinline__ uint32_t obb_round_mm_f64(float ex, float ey, float eth, float wb, float hEx, float hEy,
+                                                         float ax, float ay, float ayaw, float hl, float hw) {
+  double se, ce, sa, ca;
+  sincos((double)eth, &se, &ce);
+  sincos((double)ayaw, &sa, &ca);
+  const double cx = (double)ex + (double)wb * ce, cy = (double)ey + (double)wb * se;
+  const double rx = (double)ax - cx, ry = (double)ay - cy;
+  const double HEx = hEx, HEy = hEy, HL = hl, HW = hw;
+  const double rax = rx * ce + ry * se, ray = -rx * se + ry * ce;     // agent centre in the ego frame
+  const double rbx = rx * ca + ry * sa, rby = -rx * sa + ry * ca;     // the same offset in the agent frame
+  const double c = fabs(ce * ca + se * sa), s = fabs(sa * ce - ca * se);
+  const bool sep = (fabs(rax) > HEx + HL * c + HW * s) | (fabs(ray) > HEy + HL * s + HW * c) |
+                   (fabs(rbx) > HL + HEx * c + HEy * s) | (fabs(rby) > HW + HEx * s + HEy * c);
+  if (!sep) return 0u;
+  double best = 1.0e300;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double sx = (q & 1) ? 1.0 : -1.0, sy = (q & 2) ? 1.0 : -1.0;
+    double wx = rx + sx * HL * ca - sy * HW * sa, wy = ry + sx * HL * sa + sy * HW * ca;     // agent corner vs ego box
+    best = fmin(best, pt_box_d2_f64(wx * ce + wy * se, -wx * se + wy * ce, HEx, HEy));
+    wx = -rx + sx * HEx * ce - sy * HEy * se; wy = -ry + sx * HEx * se + sy * HEy * ce;      // ego corner vs agent box
+    best = fmin(best, pt_box_d2_f64(wx * ca + wy * sa, -wx * sa + wy * ca, HL, HW));
+  }
+  return (uint32_t)llrint(fmin(sqrt(best), 8000.0) * 1000.0);
+}
+
 __device__ __forceinline__ bool obb_hit(float rx, float ry, float c, float s, float hEx, float hEy, float hl, float hw) {
   float ac = fabsf(c), as = fabsf(s);
   float rox = fmaf(rx, c, ry * s);

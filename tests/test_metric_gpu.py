@@ -99,8 +99,11 @@ def test_summary_kernel_equals_detail_kernel(cuda_device):
     assert (~same).sum() <= max(2, 0.005 * len(same)), int((~same).sum())
     assert np.array_equal(res_d["valid"][same], res_s["valid"][same])
     ok = ((res_d["flags"] & 1) == 0) & same
-    for col in (6, 7):                                # min dce, wttc: discrete
-        assert np.array_equal(res_d["summary"][:, col], res_s["summary"][:, col])
+    # wttc: discrete.  min dce: the detail kernel re-rounds float32 rounding ties from a float64 evaluation
+    # (np.round(d, 3) next to a x.xxx5 boundary), the summary kernel does not: the last digit may differ on a few
+    assert np.array_equal(res_d["summary"][:, 7], res_s["summary"][:, 7])
+    dd = np.abs(res_d["summary"][:, 6] - res_s["summary"][:, 6])
+    assert (dd > 0).sum() <= max(2, 0.005 * len(dd)) and np.all(dd[dd > 0] < 0.0011)
     be_same = res_d["summary"][ok, 9] == res_s["summary"][ok, 9]     # bisection ties (one probe flips)
     assert (~be_same).sum() <= max(2, 0.005 * ok.sum()), int((~be_same).sum())
     # the summary kernels use the 18-instruction erfc (4e-6 relative in float32), the detail kernel CUDA's erfcf
