@@ -319,14 +319,11 @@ def run_ours(args):
 
     # ---- workload statistics for the algorithmic flop count (sample of the same bundle, on the GPU) ----
     samp = min(n_local, 20000)
-    r = eng.assess(ego_dev[:samp], want_pair=True, want_step=True)
-    torch.cuda.synchronize()
-    g_frac = float((r.step[..., 0] > 0).float().mean().item()) if T > 1 else 0.0   # lower bound of the gate fraction
-    be_pairs = float((r.pair[..., 9] > 0).float().mean().item())
-    flop_per_eval = F_BASE + F_CP * g_frac + be_pairs * 6 * T * F_BE_STEP / (T - 1)
-    del r
     st = eng.work_stats(ego_dev[:samp])
     ev = max(samp * A * (T - 1), 1)
+    g_frac = st["cp"] / ev                                  # fraction of evaluations inside the 5 m CP gate
+    be_pairs = st["be"] / max(samp * A, 1)                  # fraction of pairs with 0 < ttc < inf (BE work)
+    flop_per_eval = F_BASE + F_CP * g_frac + be_pairs * 6 * T * F_BE_STEP / (T - 1)
     executed_flop_per_eval = (FX_BOUNDS * st["visited"] + FX_OBB * st["obb"] + FX_LR4S * st["lr4s"] + FX_CP * st["cp"]
                               + FX_BE_STEP * st["be_probes"] * T) / ev
 
