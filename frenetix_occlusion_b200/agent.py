@@ -186,7 +186,19 @@ class OAPVehicleAgent(OAPAgent):
 
     @staticmethod
     def get_lanelet_velocity(pos, scenario):
-        raise NotImplementedError("velocity='lanelet' needs traffic-sign interpretation (commonroad); pass a number")
+        """agent.py:324-346: speed from the type of the lanelet the agent stands on."""
+        import warnings
+        lanelet_id = scenario.lanelet_network.find_lanelet_by_position([pos])[0][0]
+        lanelet = scenario.lanelet_network.find_lanelet_by_id(lanelet_id)
+        lanelet_type = list(lanelet.lanelet_type)[0].value
+        if lanelet_type == "urban":
+            return 30 / 3.6
+        if lanelet_type == "country":
+            return 80 / 3.6
+        if lanelet_type == "highway":
+            return 100 / 3.6
+        warnings.warn(f'OAPAgent: Lanelet type "{lanelet_type}" is not implemented yet! Default value of 50 km/h will be used!')
+        return 50 / 3.6
 
 
 class FOAgentManager:

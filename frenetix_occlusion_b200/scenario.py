@@ -83,6 +83,7 @@ class Lanelet:
         self.adj_left_same_direction: Optional[bool] = None
         self.adj_right: Optional[int] = None
         self.adj_right_same_direction: Optional[bool] = None
+        self.lanelet_type = set()      # of _Enum, like commonroad's Set[LaneletType]
 
     @property
     def polygon_vertices(self):
@@ -265,6 +266,7 @@ def load_commonroad_xml(path: str) -> Scenario:
             l.adj_left, l.adj_left_same_direction = int(al.attrib["ref"]), al.attrib.get("drivingDir") == "same"
         if ar is not None:
             l.adj_right, l.adj_right_same_direction = int(ar.attrib["ref"]), ar.attrib.get("drivingDir") == "same"
+        l.lanelet_type = {_Enum(t.text.strip()) for t in ln.findall("laneletType") if t.text}
         lanelets.append(l)
     intersections = []
     for it in root.findall("intersection"):
@@ -302,7 +304,8 @@ def scenario_to_dict(sc: Scenario, ndigits: int = 6) -> dict:
         out["lanelets"].append({"id": l.lanelet_id, "left": r(l.left_vertices), "right": r(l.right_vertices),
                                 "pred": l.predecessor, "succ": l.successor,
                                 "adj_left": [l.adj_left, l.adj_left_same_direction],
-                                "adj_right": [l.adj_right, l.adj_right_same_direction]})
+                                "adj_right": [l.adj_right, l.adj_right_same_direction],
+                                "type": sorted(t.value for t in l.lanelet_type)})
     for it in ln.intersections:
         out["intersections"].append({"id": it.intersection_id, "incomings": [
             {"id": e.incoming_id, "in": sorted(e.incoming_lanelets), "right": sorted(e.successors_right),
@@ -330,6 +333,7 @@ def scenario_from_dict(d: dict) -> Scenario:
         l.predecessor, l.successor = list(e["pred"]), list(e["succ"])
         l.adj_left, l.adj_left_same_direction = e["adj_left"]
         l.adj_right, l.adj_right_same_direction = e["adj_right"]
+        l.lanelet_type = {_Enum(t) for t in e.get("type", [])}
         lanelets.append(l)
     inters = [Intersection(it["id"], [IntersectionIncomingElement(e["id"], e["in"], e["right"], e["straight"], e["left"])
                                       for e in it["incomings"]]) for it in d.get("intersections", [])]
