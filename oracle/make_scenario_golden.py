@@ -25,8 +25,22 @@ REF_SCENARIOS = "/root/reference/example_scenarios"
 # scenario -> (time steps replayed, configured real agents); the truck/bicycle of occlusion.yaml:72-82 are
 # placed for scenario1's intersection and enter at time steps 0 and 6
 PLAN = {"scenario1": ([0, 6, 12, 18, 24], "default"), "scenario2": ([0, 10, 20, 30], None),
-        "scenario3": ([0, 5, 10, 20], None)}
+        "scenario3": ([0, 5, 10, 20], None), "parked_car": ([0, 5, 10, 15], None)}
 FAN = {"speed_factors": np.linspace(0.0, 1.3, 14).tolist(), "lateral_targets": np.linspace(-1.5, 1.5, 7).tolist()}
+
+
+def parked_car_scene() -> dict:
+    """Synthetic scene (not from the reference) that exercises the static-obstacle finder, which none of the three
+    example scenarios reaches: a straight two-lane road, a car parked half on the right lane 20 m ahead."""
+    xs = np.linspace(-20, 100, 61)
+    right = {"id": 1, "left": [[float(x), 0.0] for x in xs], "right": [[float(x), -3.5] for x in xs], "pred": [], "succ": [],
+             "adj_left": [2, False], "adj_right": [None, None], "type": ["urban"]}
+    left = {"id": 2, "left": [[float(x), 0.0] for x in xs[::-1]], "right": [[float(x), 3.5] for x in xs[::-1]], "pred": [],
+            "succ": [], "adj_left": [1, False], "adj_right": [None, None], "type": ["urban"]}
+    car = {"id": 7, "type": "parkedVehicle", "role": "static", "shape": [4.5, 1.8, 0.0, 0.0, 0.0],
+           "initial": [20.0, -2.9, 0.0, 0.0, 0], "states": None}
+    return {"dt": 0.1, "scenario_id": "parked_car", "lanelets": [right, left], "intersections": [], "obstacles": [car],
+            "planning_problem": {"id": 1, "initial": [0.0, -1.75, 0.0, 8.0, 0], "goal_lanelet": 1}}
 
 
 def run_oracle(scene: dict, timesteps, agents):
@@ -67,10 +81,14 @@ def main():
             assert json.loads(json.dumps(got)) == doc["cycles"], f"{name}: oracle no longer reproduces the golden"
             print(name, "ok")
             continue
-        scene = scenario_to_dict(load_commonroad_xml(os.path.join(REF_SCENARIOS, name + ".xml")))
+        if name == "parked_car":
+            scene = scenario_to_dict(scenario_from_dict(parked_car_scene()))
+        else:
+            scene = scenario_to_dict(load_commonroad_xml(os.path.join(REF_SCENARIOS, name + ".xml")))
         scene = json.loads(json.dumps(scene))
         cycles = run_oracle(scene, timesteps, agents)
-        doc = {"source": f"example_scenarios/{name}.xml of the reference, via oracle/make_scenario_golden.py",
+        doc = {"source": ("synthetic scene of oracle/make_scenario_golden.py" if name == "parked_car" else
+                          f"example_scenarios/{name}.xml of the reference, via oracle/make_scenario_golden.py"),
                "timesteps": timesteps, "agents": agents, "fan": FAN, "scene": scene, "cycles": cycles}
         with open(path, "w") as f:
             json.dump(doc, f, separators=(",", ":"))
