@@ -40,7 +40,7 @@ for _ in range(5):
 ms = float(np.mean(ts))
 n_edges = 4 * O + (400 if ring else 0)
 tests = F * R * n_edges
-# CPU port on a few frames
+# CPU baseline leg: the float64 port of the ray cast on a few frames (the only use of oracle/ here)
 sys.path.insert(0, ROOT)
 from oracle import visibility_oracle as VO  # noqa: E402
 rect_h, t0 = rect[:4].cpu().numpy(), time.perf_counter()
