@@ -174,8 +174,17 @@ class OAPVehicleAgent(OAPAgent):
         ro = self._rollout_path(self.reference_paths, pos, velocity, vf)
         n = int(horizon / dt) + 1
         smp = ro["sample"]
-        self._all_predictions = [self._prediction_dict(ro, j, n) for j in range(J) if smp[j] >= 0]
-        self._full_prediction = self._all_predictions[0] if self._all_predictions else None
+        valid = [j for j in range(J) if smp[j] >= 0]
+        self._all_predictions = [self._prediction_dict(ro, j, n) for j in valid]
+        # the trajectory a REAL agent drives (agent.py:348-362 with handler=None): the route whose reference path goes
+        # straightest, i.e. the smallest variance of the path heading
+        self._full_prediction = None
+        if valid:
+            def heading_var(path):
+                d = np.diff(np.asarray(path, dtype=np.float64), axis=0)
+                return float(np.var(np.unwrap(np.arctan2(d[:, 1], d[:, 0]))))
+            best = min(range(len(valid)), key=lambda q: heading_var(self.reference_paths[valid[q]]))
+            self._full_prediction = self._all_predictions[best]
         self.predictions = self._create_cr_predictions(0)
 
     def _create_cr_predictions(self, timestep) -> list:
