@@ -152,6 +152,7 @@ static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, 
   k.thr_ttc = a->thr_ttc; k.thr_dce = a->thr_dce;
   k.valid = a->valid; k.summary = a->summary; k.flags = a->flags; k.pair = a->pair; k.step = a->step;
   k.stats = stats;
+  k.claim = nullptr;
 
   cudaStream_t st = (cudaStream_t)stream;
   if (k.pair || k.step) return fo::launch_metric_detail(k, g_num_sms, st);

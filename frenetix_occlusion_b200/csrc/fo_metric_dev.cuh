@@ -29,6 +29,7 @@ struct MetricKArgs {
   float* pair;
   float* step;
   unsigned long long* stats;   // optional [8] work counters (see fo_metric_stats), NULL in production launches
+  unsigned int* claim;         // zeroed per launch: next-trajectory counter of the summary kernel (NULL = static striding)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@
 // kernel's.  Reference semantics: SURVEY.md appendix A; citations on the helpers in fo_metric_dev.cuh.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "fo_metric_dev.cuh"
 
 namespace fo {
@@ -162,11 +164,15 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const int i_hi = min(T, i_lo + L);
   unsigned long long st_dense = 0, st_obb = 0, st_lr = 0, st_cp = 0, st_be = 0, st_probe = 0;
 
-  for (int n = blockIdx.x; n < k.N; n += gridDim.x) {
+  // Trajectories are claimed from a device counter (their cost varies several-fold with the number of near agents and
+  // braking pairs); the claim for the next one is issued here and read at the bottom, so its latency is hidden.
+  __shared__ int s_next;
+  for (int n = blockIdx.x; n < k.N;) {
     // ---- stage the ego trajectory (whole team) ---------------------------------------------------
     const float* eg = k.ego + (size_t)n * T * 5;
     __syncthreads();                                   // previous trajectory fully consumed
     if (tid < 8) w.scal[tid] = 0u;
+    if (tid == 0) s_next = k.claim ? (int)(gridDim.x + atomicAdd(k.claim, 1u)) : n + (int)gridDim.x;
     __syncthreads();
     {
       float amin = 0.0f;
@@ -510,6 +516,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         sm[9] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd;
       }
     }
+    n = s_next;
   }
   if (STATS && k.stats) {
     auto wsum = [&](unsigned long long v) {
@@ -544,6 +551,37 @@ static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& sh
   W = w;
 }
 
+// Claim counters: one 4-byte slot per launch, zeroed in-stream before the kernel.  Eager launches rotate through a ring
+// (a slot is reused kClaimRing launches later); a launch recorded into a CUDA graph keeps a slot of its own for the
+// life of the process, because the graph may be replayed while later eager launches are in flight.  When the graph
+// slots run out the kernel falls back to static striding (claim == NULL).
+constexpr int kClaimRing = 1024, kClaimGraph = 3072, kMaxDev = 64;
+static unsigned int* claim_slot(cudaStream_t st) {
+  static std::mutex mu;
+  static unsigned int* pool[kMaxDev] = {};
+  static int ring_next[kMaxDev] = {}, graph_next[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> g(mu);
+  if (!pool[dev]) {
+    if (cap != cudaStreamCaptureStatusNone) return nullptr;        // no allocation while a capture is open
+    if (cudaMalloc(&pool[dev], (kClaimRing + kClaimGraph) * sizeof(unsigned int)) != cudaSuccess) {
+      cudaGetLastError();
+      pool[dev] = nullptr;
+      return nullptr;
+    }
+  }
+  if (cap != cudaStreamCaptureStatusNone) {
+    if (graph_next[dev] >= kClaimGraph) return nullptr;
+    return pool[dev] + kClaimRing + graph_next[dev]++;
+  }
+  const int s = ring_next[dev];
+  ring_next[dev] = (s + 1) % kClaimRing;
+  return pool[dev] + s;
+}
+
 template <uint32_t MASK, bool STATS, bool UNI>
 static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st);
 
@@ -569,8 +607,12 @@ static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const Sw
   FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS, UNI>, W * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const int full = num_sms * per_sm;
-  const int grid = k.N < full ? k.N : full;       // persistent: teams stride over trajectories
-  fo_metric_sweep_kernel<MASK, STATS, UNI><<<grid, W * 32, smem, st>>>(k, shape);
+  const int grid = k.N < full ? k.N : full;       // persistent: teams claim trajectories
+  MetricKArgs kk = k;
+  const char* fixed = getenv("FO_STATIC_STRIDE");          // A/B switch: teams stride over trajectories instead
+  kk.claim = (k.N > grid && !(fixed && fixed[0] == '1')) ? claim_slot(st) : nullptr;
+  if (kk.claim) FO_CUDA_TRY(cudaMemsetAsync(kk.claim, 0, sizeof(unsigned int), st));
+  fo_metric_sweep_kernel<MASK, STATS, UNI><<<grid, W * 32, smem, st>>>(kk, shape);
   count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;

@@ -200,6 +200,35 @@ def test_ragged_agent_lengths_summary(cuda_device):
         _check(parity.compare_bundle(out, res, case))
 
 
+def test_claimed_trajectories_equal_static_striding(cuda_device, monkeypatch):
+    """More trajectories than resident teams: the summary kernel hands trajectories out through a device counter
+    (zeroed in-stream per launch).  Same bits as static striding, eagerly and when the launch -- with its counter
+    reset -- is replayed from a CUDA graph."""
+    import torch
+    from frenetix_occlusion_b200.engine import AgentSet, MetricEngine
+    case = S.make_case(40000, 6, 31, seed=83)
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"])
+    eng.set_agents(AgentSet.from_case(case["agents"]))
+    ego = torch.from_numpy(np.ascontiguousarray(case["ego"], dtype=np.float32)).cuda()
+    monkeypatch.setenv("FO_STATIC_STRIDE", "1")
+    ref = eng.assess(ego)
+    torch.cuda.synchronize()
+    ref = [x.cpu().numpy().copy() for x in (ref.valid, ref.summary, ref.flags)]
+    monkeypatch.delenv("FO_STATIC_STRIDE")
+    for _ in range(3):
+        r = eng.assess(ego)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, (r.valid, r.summary, r.flags)):
+            assert np.array_equal(a, b.cpu().numpy(), equal_nan=True)
+    g, out = eng.capture(ego)
+    for _ in range(3):
+        out.summary.fill_(-1.0)
+        g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(ref, (out.valid, out.summary, out.flags)):
+            assert np.array_equal(a, b.cpu().numpy(), equal_nan=True)
+
+
 @pytest.mark.parametrize("n,a,t,detail", [(200, 12, 31, True), (60000, 4, 31, False), (7, 0, 31, False)])
 def test_host_buffer_entry_point(n, a, t, detail, cuda_device):
     """fo_metric_bundle_host (the C-ABI call a non-torch embedder makes: host pointers in, host pointers out) equals
