@@ -45,13 +45,19 @@ struct AgentTableView {
   const AgentParams* prm;
   const float4* t0;
   const float* tv;
+  const float4* aw;   // [n_windows][Ap] (x_lo, x_hi, y_lo, y_hi) of the positions at steps [8w-1, 8w+7] the agent has
+  const float* avw;   // [n_windows][Ap] max speed over steps [8w, 8w+7]
   int Ap;
 };
+
+constexpr int kWinSteps = 8;   // steps per window of the summary kernel's window filter
+__host__ __device__ inline int agent_windows(int Tp) { return (Tp + kWinSteps - 1) / kWinSteps; }
 
 __host__ __device__ inline int agent_pad(int A) { return (A + 31) & ~31; }
 __host__ __device__ inline size_t agent_table_bytes(int A, int Tp) {
   return (size_t)A * Tp * (2 * sizeof(float4) + sizeof(float2)) + (size_t)A * sizeof(AgentParams) +
-         (size_t)agent_pad(A) * Tp * (sizeof(float4) + sizeof(float));
+         (size_t)agent_pad(A) * Tp * (sizeof(float4) + sizeof(float)) +
+         (size_t)agent_pad(A) * agent_windows(Tp) * (sizeof(float4) + sizeof(float));
 }
 __host__ __device__ inline AgentTableView agent_table_view(const void* base, int A, int Tp) {
   AgentTableView v;
@@ -61,7 +67,9 @@ __host__ __device__ inline AgentTableView agent_table_view(const void* base, int
   v.t0 = reinterpret_cast<const float4*>(v.prm + A);
   v.Ap = agent_pad(A);
   v.tv = reinterpret_cast<const float*>(v.t0 + (size_t)v.Ap * Tp);
-  v.s2 = reinterpret_cast<const float2*>(v.tv + (size_t)v.Ap * Tp);
+  v.aw = reinterpret_cast<const float4*>(v.tv + (size_t)v.Ap * Tp);
+  v.avw = reinterpret_cast<const float*>(v.aw + (size_t)v.Ap * agent_windows(Tp));
+  v.s2 = reinterpret_cast<const float2*>(v.avw + (size_t)v.Ap * agent_windows(Tp));
   return v;
 }
 

@@ -28,9 +28,25 @@ __device__ __forceinline__ int protection_model(int kind) {  // harm_model.py:15
 }
 
 __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, float4* s1, float2* s2, AgentParams* prm,
-                                      float4* t0, float* tv, int Ap) {
+                                      float4* t0, float* tv, float4* aw, float* avw, int Ap) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int A = raw.n_agents, Tp = raw.t_stride;
+  const int nW = agent_windows(Tp);
+  if (idx < Ap * nW) {                       // window boxes for the summary kernel's filter
+    const int a = idx / nW, wi = idx - a * nW;
+    float xl = 1e30f, xh = -1e30f, yl = 1e30f, yh = -1e30f, vm = 0.0f;
+    if (a < A) {
+      const int nS = min(raw.n_states[a], Tp);
+      const int lo = wi * kWinSteps;
+      for (int i = max(lo - 1, 0); i < min(lo + kWinSteps, nS); ++i) {
+        const float x = raw.x[a * Tp + i], y = raw.y[a * Tp + i];
+        xl = fminf(xl, x); xh = fmaxf(xh, x); yl = fminf(yl, y); yh = fmaxf(yh, y);
+        if (i >= lo) vm = fmaxf(vm, fabsf(raw.v[a * Tp + i]));
+      }
+    }
+    aw[(size_t)wi * Ap + a] = make_float4(xl, xh, yl, yh);
+    avw[(size_t)wi * Ap + a] = vm;
+  }
   if (idx >= A * Tp && idx < Ap * Tp) {      // padding agents of the time-major copy
     const int a = idx / Tp, i = idx - a * Tp;
     t0[(size_t)i * Ap + a] = make_float4(0, 0, 1, 0);
@@ -100,7 +116,8 @@ extern "C" int fo_agents_pack(const FoAgentsRaw* raw, const FoVehicle* vehicle, 
   const int total = v.Ap * Tp;
   fo::fo_agents_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       *raw, vehicle->mass, const_cast<float4*>(v.s0), const_cast<float4*>(v.s1), const_cast<float2*>(v.s2),
-      const_cast<fo::AgentParams*>(v.prm), const_cast<float4*>(v.t0), const_cast<float*>(v.tv), v.Ap);
+      const_cast<fo::AgentParams*>(v.prm), const_cast<float4*>(v.t0), const_cast<float*>(v.tv),
+      const_cast<float4*>(v.aw), const_cast<float*>(v.avw), v.Ap);
   fo::count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;

@@ -44,16 +44,21 @@ constexpr int kSwQueue = 64;
 #define FO_SW_UNROLL 1
 #endif
 constexpr int kSwUnroll = FO_SW_UNROLL;
+constexpr int kSwWinQueue = 64;   // <= 31 left over + 32 from one filter step
+constexpr int kSwInvBytes = (kBeBuckets + 1 + 15) & ~15;   // arc-length bucket table, padded so that what follows stays 16-byte aligned
 
 __host__ __device__ inline size_t sweep_smem_bytes(int T, int W) {
-  size_t b = (size_t)kSwTile * 8                 // pairkey
-             + (size_t)T * (16 + 8 + 4)          // egoA, egoB, dist
-             + (size_t)kSwTile * 4               // colfirst
+  const size_t nW = (size_t)agent_windows(T);
+  size_t b = (size_t)kSwTile * (8 + 4 + 2)       // pairkey, colfirst, BE pair list
+             + 8 * 4 + kSwInvBytes               // scalars, arc-length bucket table
+             + (size_t)kSwWinQueue * 2           // (agent, window) work items of the window filter
              + (size_t)W * 2 * kSwQueue * 4      // per-warp near / cp queues
              + (size_t)W * 2 * 32 * 4            // pooled leftovers
              + (size_t)W * 16 * 4                // per-warp partial results
-             + (size_t)kSwTile * 2               // BE pair list
-             + 8 * 4 + kBeBuckets + 16;
+             + nW * 16                           // ego window boxes
+             + (size_t)T * (16 + 8)              // egoA, egoB
+             + (size_t)((T + 3) & ~3) * 4        // dist
+             + nW * 4;                           // ego window speeds
   return (b + 15) & ~(size_t)15;
 }
 
@@ -71,23 +76,31 @@ struct SweepSmem {
   uint32_t* scal;               // [8]: 0 |min(a, 0)| (float bits), 1 BE list length, 2 pooled near, 3 pooled cp
   uint16_t* be_list;            // [kSwTile]
   uint8_t* inv;                 // [kBeBuckets + 1]
+  uint16_t* q_win;              // [kSwWinQueue] (agent-in-tile << 8 | window) items that passed the window filter
+  float4* ew;                   // [windows] (x_lo, x_hi, y_lo, y_hi) of the ego reference point and centre over a window
+  float* evw;                   // [windows] max |v| of the ego over a window
 };
 
+// Fixed-size arrays first, then the per-warp ones, then the T-sized ones: every hot array except egoB / dist sits at
+// a compile-time offset when W is a constant (the one-warp throughput shape), so its address is an immediate.
 __device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int W) {
   SweepSmem w;
   w.pairkey = reinterpret_cast<unsigned long long*>(base);
-  w.egoA = reinterpret_cast<float4*>(w.pairkey + kSwTile);
-  w.egoB = reinterpret_cast<float2*>(w.egoA + T);
-  w.dist = reinterpret_cast<float*>(w.egoB + T);
-  w.colfirst = reinterpret_cast<uint32_t*>(w.dist + T);
-  w.q_near = w.colfirst + kSwTile;
+  w.colfirst = reinterpret_cast<uint32_t*>(w.pairkey + kSwTile);
+  w.be_list = reinterpret_cast<uint16_t*>(w.colfirst + kSwTile);
+  w.scal = reinterpret_cast<uint32_t*>(w.be_list + kSwTile);
+  w.inv = reinterpret_cast<uint8_t*>(w.scal + 8);
+  w.q_win = reinterpret_cast<uint16_t*>(w.inv + kSwInvBytes);
+  w.q_near = reinterpret_cast<uint32_t*>(w.q_win + kSwWinQueue);
   w.q_cp = w.q_near + (size_t)W * kSwQueue;
   w.pool_near = w.q_cp + (size_t)W * kSwQueue;
   w.pool_cp = w.pool_near + (size_t)W * 32;
   w.red = reinterpret_cast<float*>(w.pool_cp + (size_t)W * 32);
-  w.scal = reinterpret_cast<uint32_t*>(w.red + (size_t)W * 16);
-  w.be_list = reinterpret_cast<uint16_t*>(w.scal + 8);
-  w.inv = reinterpret_cast<uint8_t*>(w.be_list + kSwTile);
+  w.ew = reinterpret_cast<float4*>(w.red + (size_t)W * 16);
+  w.egoA = w.ew + agent_windows(T);
+  w.egoB = reinterpret_cast<float2*>(w.egoA + T);
+  w.dist = reinterpret_cast<float*>(w.egoB + T);
+  w.evw = w.dist + ((T + 3) & ~3);
   return w;
 }
 
@@ -112,6 +125,14 @@ __device__ __forceinline__ float warp_max_signed(float v) { return ord2f(__reduc
 
 __device__ __forceinline__ float sw_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
+// impact-angle class coefficients of both parties (one copy in the kernel: atan2f is ~150 instructions and the harm
+// logits are needed at five inlined sites; the kernel is instruction-cache-bound, not call-bound)
+static __device__ __noinline__ float2 sw_lr4s_pair(float dyr, float dxr, float th, float psi, float side, float rear) {
+  const float PI_F = 3.14159265358979323846f;
+  const float rel = atan2f(dyr, dxr);
+  return make_float2(lr4s_coef(rel - th, side, rear), lr4s_coef(PI_F + rel - psi, side, rear));
+}
+
 // exact harm logits for one (agent, state) -- harm_model.py:81-105, logistic_regression.py:35-48,71-73
 __device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, float ke, float ko, float dv, float dxr,
                                                float dyr, float th, float psi, float& ze, float& zo) {
@@ -119,10 +140,9 @@ __device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, 
     ze = fmaf(k.hc.ia_speed * ke, dv, k.hc.ia_const);
     zo = fmaf(k.hc.ped_speed * ko, dv, -k.hc.ped_const);
   } else if (model == 1) {
-    const float PI_F = 3.14159265358979323846f;
-    const float rel = atan2f(dyr, dxr);
-    ze = fmaf(k.hc.rs_speed * ke, dv, k.hc.rs_const) + lr4s_coef(rel - th, k.hc.rs_side, k.hc.rs_rear);
-    zo = fmaf(k.hc.rs_speed * ko, dv, k.hc.rs_const) + lr4s_coef(PI_F + rel - psi, k.hc.rs_side, k.hc.rs_rear);
+    const float2 cls = sw_lr4s_pair(dyr, dxr, th, psi, k.hc.rs_side, k.hc.rs_rear);
+    ze = fmaf(k.hc.rs_speed * ke, dv, k.hc.rs_const) + cls.x;
+    zo = fmaf(k.hc.rs_speed * ko, dv, k.hc.rs_const) + cls.y;
   } else {
     ze = CUDART_INF_F;
     zo = CUDART_INF_F;
@@ -143,7 +163,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, wib = tid >> 5, W = nthr >> 5;
   const int T = k.T;
-  const SweepSmem w = sweep_smem(smem_raw, T, W);
+  const SweepSmem w = sweep_smem(smem_raw, T, UNI ? 1 : W);
   uint32_t* const q_near = w.q_near + wib * kSwQueue;
   uint32_t* const q_cp = w.q_cp + wib * kSwQueue;
   const uint32_t mm = MASK ? MASK : k.mmask;
@@ -160,9 +180,9 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const int la = lane & (group - 1), ls = lane >> lg;
   const int n_slices = W * (32 >> lg);
   const int L = (T + n_slices - 1) / n_slices;    // steps per slice
-  const int i_lo = (wib * (32 >> lg) + ls) * L;
-  const int i_hi = min(T, i_lo + L);
-  unsigned long long st_dense = 0, st_obb = 0, st_lr = 0, st_cp = 0, st_be = 0, st_probe = 0;
+  const int s_lo = (wib * (32 >> lg) + ls) * L;
+  const int s_hi = min(T, s_lo + L);
+  unsigned long long st_dense = 0, st_obb = 0, st_lr = 0, st_cp = 0, st_be = 0, st_probe = 0, st_win = 0, st_wkeep = 0;
 
   // Trajectories are claimed from a device counter (their cost varies several-fold with the number of near agents and
   // braking pairs); the claim for the next one is issued here and read at the bottom, so its latency is hidden.
@@ -186,6 +206,21 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         w.egoB[i] = make_float2(th, v);
       }
       if (do_be && amin < 0.0f) atomicMax(&w.scal[0], __float_as_uint(-amin));   // |min(min a, 0)|, be.py:68
+    }
+    if (UNI) {                                         // boxes of the ego over windows of kWinSteps steps
+      __syncthreads();
+      if (tid * kWinSteps < T) {
+        float xl = 1e30f, xh = -1e30f, yl = 1e30f, yh = -1e30f, vm = 0.0f;
+        for (int i = tid * kWinSteps; i < min(T, (tid + 1) * kWinSteps); ++i) {
+          const float4 EA = w.egoA[i];
+          const float cx = fmaf(k.wb, EA.z, EA.x), cy = fmaf(k.wb, EA.w, EA.y);     // box centre (dce.py:57-60)
+          xl = fminf(xl, fminf(EA.x, cx)); xh = fmaxf(xh, fmaxf(EA.x, cx));
+          yl = fminf(yl, fminf(EA.y, cy)); yh = fmaxf(yh, fmaxf(EA.y, cy));
+          vm = fmaxf(vm, fabsf(w.egoB[i].y));
+        }
+        w.ew[tid] = make_float4(xl, xh, yl, yh);
+        w.evw[tid] = vm;
+      }
     }
 
     uint32_t rmin = 0xffffffu;                       // warp-uniform running min of round(d * 1000)
@@ -305,16 +340,15 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       };
 
       // ---- dense sweep: lane groups of `group` agents x the steps of this lane's slice ------------------
-      for (int sub = 0; sub < nAt; sub += group) {
-        const int al = sub + la;
+      // flush (warp-uniform): no lane has work; drain what is left in the two queues through the same inlined drains
+      auto run_group = [&](const int al, const bool alive, const int i_lo, const int i_hi, const bool flush) {
         const int a = a0 + al;
-        const bool alive = al < nAt;
         AgentParams P;
         P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
         if (alive) P = sw_load_params(k.tab.prm + a);
         const int nS = min(P.n_states, i_hi);             // this lane evaluates steps [i_lo, nS)
         const int nH = min(nS, T - 1);                    // harm is evaluated at steps < min(T-1, n_states)
-        const int n_it = (int)__reduce_max_sync(kFull, (unsigned)max(nS - i_lo, 0));
+        const int n_it = flush ? 1 : (int)__reduce_max_sync(kFull, (unsigned)max(nS - i_lo, 0));
         const bool is_m0 = P.model == 0;
         is_m1 = P.model == 1;
         // harm logit = ks * dv + kc (+ LR4S class coefficient for protected agents)
@@ -330,8 +364,8 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const uint32_t item0 = (uint32_t)al << 8;
         // time-major table, agents padded to a multiple of 32: the agent index is always in bounds; rows are only
         // read for steps the agent has (i < n_states <= t_stride)
-        const float4* t0 = k.tab.t0 + (size_t)i_lo * Ap + (a0 + sub + la);
-        const float* tv = k.tab.tv + (size_t)i_lo * Ap + (a0 + sub + la);
+        const float4* t0 = k.tab.t0 + (size_t)i_lo * Ap + a;
+        const float* tv = k.tab.tv + (size_t)i_lo * Ap + a;
         float pxp = 0.0f, pyp = 0.0f;                      // position at i-1 (collision_probability.py:52)
         if (do_cp && i_lo >= 1 && i_lo < nS) { const float4 sp = __ldg(t0 - Ap); pxp = sp.x; pyp = sp.y; }
         float acc_dv2 = -1.0f;                             // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
@@ -341,9 +375,8 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           const bool live = i < nS;
           float4 s0 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
           float va = 0.0f;
-          if (UNI) { s0 = __ldg(t0); va = __ldg(tv); }      // i < max n_states <= t_stride: the row exists (padding zeroed)
-          else if (live) { s0 = __ldg(t0); va = __ldg(tv); }
-          const int ie = UNI ? i : min(i, T - 1);
+          if (live) { s0 = __ldg(t0); va = __ldg(tv); }
+          const int ie = min(i, T - 1);
           const float4 EA = w.egoA[ie];
           const float ve = w.egoB[ie].y;
           const float dxr = s0.x - EA.x, dyr = s0.y - EA.y;
@@ -369,19 +402,19 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           pxp = s0.x; pyp = s0.y;
           const bool near = need_obb | need_lr;
           unsigned b = __ballot_sync(kFull, near);
-          if (b) {
+          if (b || flush) {
             if (near) q_near[qn + __popc(b & lt_mask)] = item0 | (uint32_t)i | (need_obb ? 0x40000000u : 0u) |
                                                        (need_lr ? 0x80000000u : 0u);
             qn += __popc(b);
             __syncwarp();
-            if (qn >= 32) { qn -= 32; drain_near(q_near + qn, 32); }
+            if (qn >= 32 || (flush && qn > 0)) { const int c = min(qn, 32); qn -= c; drain_near(q_near + qn, c); }
           }
           b = __ballot_sync(kFull, ingate);
-          if (b) {
+          if (b || flush) {
             if (ingate) q_cp[qc + __popc(b & lt_mask)] = item0 | (uint32_t)i;
             qc += __popc(b);
             __syncwarp();
-            if (qc >= 32) { qc -= 32; drain_cp(q_cp + qc, 32); }
+            if (qc >= 32 || (flush && qc > 0)) { const int c = min(qc, 32); qc -= c; drain_cp(q_cp + qc, c); }
           }
           if (STATS) st_dense += live;
         }
@@ -394,10 +427,83 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           zb_e = fmaxf(zb_e, warp_max_signed(acc_ze));
           zb_o = fmaxf(zb_o, warp_max_signed(acc_zo));
         }
+      };
+
+      if (UNI) {
+        // Window filter (one warp, >= 32 agents per pass).  lane = agent: every window of kWinSteps steps is tested with
+        // the boxes of the two paths over that window -- gap between the boxes against the reach of the distance and
+        // 5 m-gate bounds, sum of the top speeds against the logit bound -- and only the (agent, window) items that can
+        // still change a result are queued; full warps of items then run the per-step loop, lane = item.
+        int sub = 0, wi = 0, qw = 0, f_nS = 0, f_nH = 0, f_nW = 0;
+        float f_reach2 = 0.0f, f_thr2 = -1.0f;
+        bool more = nAt > 0, stale = true, flushed = false;
+        for (;;) {
+          while (more && qw < 32) {
+            const int al = sub + lane;
+            if (stale) {
+              AgentParams P;
+              P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
+              if (al < nAt) P = sw_load_params(k.tab.prm + a0 + al);
+              f_nS = min(P.n_states, T);
+              f_nH = min(f_nS, T - 1);
+              f_nW = (int)__reduce_max_sync(kFull, (unsigned)((f_nS + kWinSteps - 1) / kWinSteps));
+              // reach of the per-step distance bounds (+1 mm: the per-step code rounds its differences differently)
+              const float lim = do_dce ? rE + P.pad + (float)(rmin + 2u) * 0.001f + 0.001f : 0.0f;
+              const float gate = do_cp ? 5.001f + P.hlb : 0.0f;
+              const float reach = fmaxf(lim, gate);
+              f_reach2 = reach * reach;
+              float t2 = CUDART_INF_F;                      // harm logit <= ks (|v_e| + |v_a|) + kc (+ cmax)
+              if (do_hr && P.model != 2) {
+                const bool m0 = P.model == 0;
+                const float cm = m0 ? 0.0f : cmax;
+                const float fse = (m0 ? k.hc.ia_speed : k.hc.rs_speed) * P.ke;
+                const float fso = (m0 ? k.hc.ped_speed : k.hc.rs_speed) * P.ko;
+                const float fce = (m0 ? k.hc.ia_const : k.hc.rs_const) + cm;
+                const float fco = (m0 ? -k.hc.ped_const : k.hc.rs_const) + cm;
+                const float ze_m = fmaxf(zb_e, acc_ze), zo_m = fmaxf(zb_o, acc_zo);
+                const float te = (fse > 0.0f) ? __fdividef(ze_m - fce, fse) : ((fce > ze_m) ? -1.0f : CUDART_INF_F);
+                const float to = (fso > 0.0f) ? __fdividef(zo_m - fco, fso) : ((fco > zo_m) ? -1.0f : CUDART_INF_F);
+                const float tm = fminf(te, to);
+                t2 = (tm > 0.0f) ? tm * tm * 0.99999f : -1.0f;
+              }
+              f_thr2 = t2;
+              stale = false;
+            }
+            if (wi < f_nW) {
+              const float4 B = __ldg(k.tab.aw + (size_t)wi * Ap + a0 + al);
+              const float av = __ldg(k.tab.avw + (size_t)wi * Ap + a0 + al);
+              const float4 E = w.ew[wi];
+              const float dvu = w.evw[wi] + av;
+              const float gx = fmaxf(fmaxf(B.x - E.y, E.x - B.y), 0.0f), gy = fmaxf(fmaxf(B.z - E.w, E.z - B.w), 0.0f);
+              const int i0 = wi * kWinSteps;
+              const bool keep = (i0 < f_nS) & ((fmaf(gx, gx, gy * gy) < f_reach2) | ((i0 < f_nH) & (dvu * dvu > f_thr2)));
+              const unsigned b = __ballot_sync(kFull, keep);
+              if (keep) w.q_win[qw + __popc(b & lt_mask)] = (uint16_t)((al << 8) | wi);
+              qw += __popc(b);
+              if (STATS) { st_win += (i0 < f_nS); st_wkeep += keep; }
+            }
+            if (++wi >= f_nW) { wi = 0; sub += 32; more = sub < nAt; stale = true; }
+          }
+          bool flush = false;
+          if (qw == 0) {                                // all items done: one more pass drains the two queues
+            if (flushed) break;
+            flushed = flush = true;
+          }
+          const int cnt = min(qw, 32);
+          qw -= cnt;
+          __syncwarp();
+          const uint32_t it = (lane < cnt) ? (uint32_t)w.q_win[qw + lane] : 0u;
+          __syncwarp();
+          const int i0 = (int)(it & 0xffu) * kWinSteps;
+          run_group((int)(it >> 8), lane < cnt, i0, min(T, i0 + kWinSteps), flush);
+          stale = true;
+        }
+      } else {
+        for (int sub = 0; sub < nAt; sub += group) run_group(sub + la, sub + la < nAt, s_lo, s_hi, false);
       }
       // ---- pool what is left in the per-warp queues across the team and drain it cooperatively --------------
       is_m1 = false;
-      {
+      if (!UNI) {
         unsigned base_n = 0, base_c = 0;
         if (lane == 0) {
           if (qn > 0) base_n = atomicAdd(&w.scal[2], (unsigned)qn);
@@ -523,11 +629,13 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
       return v;
     };
+    const unsigned long long s6 = wsum(st_win), s7 = wsum(st_wkeep);
     const unsigned long long s0 = wsum(st_dense), s1 = wsum(st_obb), s2 = wsum(st_lr), s3 = wsum(st_cp);
     st_be = wsum(st_be); st_probe = wsum(st_probe);
     if (lane == 0) {
       atomicAdd(&k.stats[0], s0); atomicAdd(&k.stats[1], s1); atomicAdd(&k.stats[2], s2); atomicAdd(&k.stats[3], s3);
       atomicAdd(&k.stats[4], st_be); atomicAdd(&k.stats[5], st_probe);
+      atomicAdd(&k.stats[6], s6); atomicAdd(&k.stats[7], s7);
     }
   }
 }
@@ -546,7 +654,7 @@ static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& sh
   if (w > max_w) w = max_w;
   if (w > kSwMaxWarps) w = kSwMaxWarps;
   if (w < 1) w = 1;
-  static const char* forced = getenv("FO_TEAM_WARPS");           // measurement switch
+  const char* forced = getenv("FO_TEAM_WARPS");                  // measurement / test switch
   if (forced) { int f = atoi(forced); if (f >= 1 && f <= kSwMaxWarps) w = f; }
   W = w;
 }

@@ -262,7 +262,8 @@ class MetricEngine:
             cnt = torch.zeros(8, dtype=torch.int64, device=dev)
             L.check(L.lib.fo_metric_stats(C.byref(a), C.c_void_p(cnt.data_ptr()), self._stream()), "fo_metric_stats")
             c = cnt.cpu().tolist()
-        return {"visited": c[0], "obb": c[1], "lr4s": c[2], "cp": c[3], "be": c[4], "be_probes": c[5]}
+        return {"visited": c[0], "obb": c[1], "lr4s": c[2], "cp": c[3], "be": c[4], "be_probes": c[5],
+                "windows": c[6], "windows_kept": c[7]}
 
     def assess(self, ego, want_pair: bool = False, want_step: bool = False, out: Optional[BundleResult] = None
                ) -> BundleResult:

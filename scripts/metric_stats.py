@@ -22,3 +22,6 @@ print({k: v for k, v in st.items()}, "evals", evals)
 for k in ("obb", "lr4s", "cp"):
     print(k, "per visited evaluation:", st[k] / max(st["visited"], 1))
 print("be pairs per pair:", st["be"] / (n * a), "probes per be:", st["be_probes"] / max(st["be"], 1))
+if st.get("windows"):
+    print("window filter: kept", st["windows_kept"] / st["windows"], "of", st["windows"], "(agent, window) items;",
+          "visited", st["visited"] / evals, "of the evaluations")

@@ -126,6 +126,19 @@ def test_summary_kernel_matches_oracle(seed, n, a, t, cuda_device):
     _check(parity.compare_bundle(out, res, case))
 
 
+@pytest.mark.parametrize("seed,n,a,t,metrics", [(35, 300, 32, 31, None), (36, 120, 300, 51, None), (37, 200, 20, 12, None),
+                                                (38, 150, 64, 97, None), (39, 200, 40, 31, ["hr", "cp"]),
+                                                (40, 200, 40, 31, ["dce", "ttc", "wttc"])])
+def test_window_filter_shape_matches_oracle(seed, n, a, t, metrics, cuda_device, monkeypatch):
+    """One warp per trajectory and >= 17 agents is the throughput shape with the (agent, 8-step window) filter in
+    front of the per-step loop; bundles this small normally take the multi-warp shape, so force it."""
+    monkeypatch.setenv("FO_TEAM_WARPS", "1")
+    case = S.make_case(n, a, t, seed=seed, activated_metrics=metrics)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    _check(parity.compare_bundle(out, res, case))
+
+
 @pytest.mark.parametrize("metrics,thr", [
     (["hr", "ttc", "ttce", "dce", "wttc", "cp"], {"harm": 0.1, "risk": 1, "be": None, "cp": None, "ttc": None, "dce": None}),
     (["dce", "ttc"], {"harm": None, "risk": None, "be": None, "cp": None, "ttc": 1.2, "dce": 0.75}),
