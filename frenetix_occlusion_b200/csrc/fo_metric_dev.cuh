@@ -202,6 +202,7 @@ struct BeView {
 
 static __device__ __noinline__ void be_prepare(const BeView w, int T, int lane) {
   float carry = 0.0f;
+#pragma unroll 1
   for (int i0 = 0; i0 < T; i0 += 32) {
     const int i = i0 + lane;
     float seg = 0.0f;
@@ -220,6 +221,7 @@ static __device__ __noinline__ void be_prepare(const BeView w, int T, int lane) 
   }
   __syncwarp();
   const float bw = w.dist[T - 1] / (float)kBeBuckets;
+#pragma unroll 1
   for (int b = lane; b <= kBeBuckets; b += 32) {
     const float q = (b == kBeBuckets) ? CUDART_INF_F : (float)b * bw;
     int lo_j = 0, hi_j = T - 1;
@@ -253,6 +255,7 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
   const float4 pre0 = (lane < nA) ? __ldg(sa + lane) : make_float4(0, 0, 1, 0);
   const float4 pre1 = (32 + lane < nA) ? __ldg(sa + 32 + lane) : make_float4(0, 0, 1, 0);
   float lo = lo0, hi = 5.0f, cur = 0.0f;
+#pragma unroll 1
   for (int it = 0; it < 10; ++it) {
     cur = 0.5f * (lo + hi);
     ++probes;
@@ -260,6 +263,7 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
     const float mpos = (step > 0.0f) ? fmaxf(floorf(__fdividef(v1, step)) + 1.0f, 0.0f) : 1.0e9f;
     if (be_arclen(k.dt, v0, v1, step, mpos, T - 1) > dmax) { range_err = true; return CUDART_NAN_F; }
     bool any_hit = false;
+#pragma unroll 1
     for (int i0 = 0; i0 < nA && !any_hit; i0 += 32) {
       const int i = i0 + lane;
       bool hit = false;

@@ -211,6 +211,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       __syncthreads();
       if (tid * kWinSteps < T) {
         float xl = 1e30f, xh = -1e30f, yl = 1e30f, yh = -1e30f, vm = 0.0f;
+#pragma unroll 1
         for (int i = tid * kWinSteps; i < min(T, (tid + 1) * kWinSteps); ++i) {
           const float4 EA = w.egoA[i];
           const float cx = fmaf(k.wb, EA.z, EA.x), cy = fmaf(k.wb, EA.w, EA.y);     // box centre (dce.py:57-60)
