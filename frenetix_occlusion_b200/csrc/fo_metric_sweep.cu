@@ -437,6 +437,11 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         // still change a result are queued; full warps of items then run the per-step loop, lane = item.
         int sub = 0, wi = 0, qw = 0, f_nS = 0, f_nH = 0, f_nW = 0;
         float f_reach2 = 0.0f, f_thr2 = -1.0f;
+        // cursors into the window tables; re-derived whenever the per-agent state is (they do not live across run_group)
+        const float4* awp = k.tab.aw;
+        const float* avp = k.tab.avw;
+        const float4* ewp = w.ew;
+        const float* evp = w.evw;
         bool more = nAt > 0, stale = true, flushed = false;
         for (;;) {
           while (more && qw < 32) {
@@ -468,13 +473,18 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
                 t2 = (tm > 0.0f) ? tm * tm * 0.99999f : -1.0f;
               }
               f_thr2 = t2;
+              awp = k.tab.aw + (size_t)wi * Ap + a0 + al;
+              avp = k.tab.avw + (size_t)wi * Ap + a0 + al;
+              ewp = w.ew + wi;
+              evp = w.evw + wi;
               stale = false;
             }
             if (wi < f_nW) {
-              const float4 B = __ldg(k.tab.aw + (size_t)wi * Ap + a0 + al);
-              const float av = __ldg(k.tab.avw + (size_t)wi * Ap + a0 + al);
-              const float4 E = w.ew[wi];
-              const float dvu = w.evw[wi] + av;
+              const float4 B = __ldg(awp);
+              const float av = __ldg(avp);
+              const float4 E = *ewp;
+              const float dvu = *evp + av;
+              awp += Ap; avp += Ap; ++ewp; ++evp;
               const float gx = fmaxf(fmaxf(B.x - E.y, E.x - B.y), 0.0f), gy = fmaxf(fmaxf(B.z - E.w, E.z - B.w), 0.0f);
               const int i0 = wi * kWinSteps;
               const bool keep = (i0 < f_nS) & ((fmaf(gx, gx, gy * gy) < f_reach2) | ((i0 < f_nH) & (dvu * dvu > f_thr2)));
