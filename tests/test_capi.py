@@ -26,8 +26,8 @@ def test_every_declared_symbol_is_exported():
 def test_argument_validation_without_device():
     from frenetix_occlusion_b200 import _lib as L
     assert L.lib.fo_version() == 1
-    assert L.lib.fo_agent_table_bytes(256, 51) == 256 * 51 * 40 + 256 * 32 + 256 * 51 * 20
-    assert L.lib.fo_agent_table_bytes(33, 31) == 33 * 31 * 40 + 33 * 32 + 64 * 31 * 20
+    assert L.lib.fo_agent_table_bytes(256, 51) == 256 * 51 * 40 + 256 * 32 + 256 * 51 * 20 + 256 * 7 * 20   # + 7 windows of 8 steps
+    assert L.lib.fo_agent_table_bytes(33, 31) == 33 * 31 * 40 + 33 * 32 + 64 * 31 * 20 + 64 * 4 * 20
     assert L.lib.fo_metric_bundle(None, None) == -1
     assert b"NULL" in L.lib.fo_last_error()
     a = L.FoMetricArgs()
