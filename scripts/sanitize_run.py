@@ -22,6 +22,16 @@ for (n, a, t) in [(40, 32, 31), (300, 8, 31), (12, 300, 51), (9000, 3, 31), (5, 
     st = eng.work_stats(case["ego"][: min(n, 50)])
     torch.cuda.synchronize()
     print("metric", n, a, t, int(r.valid.sum()), st["cp"])
+os.environ["FO_TEAM_WARPS"] = "1"      # one-warp shape: window filter, queue flush; 6000 trajectories: claim counter
+for (n, a, t) in [(60, 40, 51), (30, 300, 31), (6000, 20, 12), (20, 33, 97)]:
+    case = S.make_case(n, a, t, seed=n)
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"])
+    eng.set_agents(AgentSet.from_case(case["agents"]))
+    r = eng.assess(case["ego"])
+    st = eng.work_stats(case["ego"][: min(n, 50)])
+    torch.cuda.synchronize()
+    print("metric/window filter", n, a, t, int(r.valid.sum()), st["windows_kept"], st["windows"])
+del os.environ["FO_TEAM_WARPS"]
 rect = torch.from_numpy(S.obstacle_frames(3, 40)).cuda()
 flags = torch.ones((3, 40), dtype=torch.uint8, device="cuda")
 flags[:, ::7] |= 2
