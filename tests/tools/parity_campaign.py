@@ -17,13 +17,20 @@ import parity  # noqa: E402
 rng = np.random.default_rng(2024)
 shapes = [(400, 32, 31), (150, 64, 51), (600, 6, 31), (80, 256, 51), (250, 20, 31), (1000, 3, 31)]
 agg = {"cases": 0, "pairs": 0, "trajectories": 0, "evaluations": 0, "hard_failures": [], "mask_mismatch": 0,
-       "ties_detail": {}, "ties_summary": {}, "cp_max_rel": 0.0}
+       "ties_detail": {}, "ties_summary": {}, "ties_summary_one_warp_window_filter": {}, "cp_max_rel": 0.0}
 for rep_i in range(4):
     for (n, a, t) in shapes:
         seed = int(rng.integers(1, 1 << 30))
         case = S.make_case(n, a, t, seed=seed)
         out = MO.evaluate_bundle(case)
-        for detail, key in ((True, "ties_detail"), (False, "ties_summary")):
+        arms = [(True, "ties_detail", None), (False, "ties_summary", None)]
+        if a >= 17:      # the throughput shape (one warp per trajectory, window filter); small bundles need it forced
+            arms.append((False, "ties_summary_one_warp_window_filter", "1"))
+        for detail, key, team in arms:
+            if team is None:
+                os.environ.pop("FO_TEAM_WARPS", None)
+            else:
+                os.environ["FO_TEAM_WARPS"] = team
             res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
             rep = parity.compare_bundle(out, res, case)
             for k, v in rep["ties"].items():
@@ -31,7 +38,7 @@ for rep_i in range(4):
             agg["mask_mismatch"] += rep.get("mask_mismatch", 0)
             agg["cp_max_rel"] = max(agg["cp_max_rel"], rep.get("cp_max_rel", 0.0))
             if rep["fail"]:
-                agg["hard_failures"].append({"seed": seed, "shape": [n, a, t], "detail": detail, "fail": rep["fail"][:3]})
+                agg["hard_failures"].append({"seed": seed, "shape": [n, a, t], "arm": key, "fail": rep["fail"][:3]})
         agg["cases"] += 1
         agg["pairs"] += n * a
         agg["trajectories"] += n
