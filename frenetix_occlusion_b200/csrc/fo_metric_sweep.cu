@@ -3,8 +3,8 @@
 // Emits what the planner consumes per trajectory: the validity mask (metrics/metric.py:50-98), ten summary scalars
 // and the flags.  Mapping (B200-first, not a translation of the reference's Python loops):
 //
-//   * one CTA = one TEAM of W warps owns one trajectory (persistent: teams stride over the bundle); its T ego states
-//     are staged once in shared memory.  W = 1 for sweeps that oversubscribe the machine; W up to 8 when the whole
+//   * one CTA = one TEAM of W warps owns one trajectory (persistent: teams claim trajectories from a per-launch device
+//     counter, their cost varies several-fold); its T ego states are staged once in shared memory.  W = 1 for sweeps that oversubscribe the machine; W up to 8 when the whole
 //     bundle fits in one wave, because then the latency of a bundle is the critical path of its slowest trajectory;
 //   * LANE = (AGENT, TIME SLICE), the loop runs over the steps of the slice: with >= 32 agents a warp holds 32 agents
 //     and one slice (the time index is warp-uniform, the ego state one broadcast LDS); with fewer agents the 32 lanes
@@ -19,13 +19,18 @@
 //     all lanes active: the exact oriented-box distance (dce.py:75-79) and/or the LR4S impact-angle logit
 //     (logistic_regression.py:35-48), and the 9-term Gaussian box mass (collision_probability.py:94-122).  What is
 //     left in the queues at the end of an agent tile is pooled across the team and drained cooperatively;
+//   * in the one-warp shape with >= 17 agents (UNI, the throughput case) a WINDOW FILTER runs in front of that loop:
+//     lane = agent, one test per (agent, window of 8 steps) of the two paths' bounding boxes and top speeds against
+//     the same bounds; surviving (agent, window) items are queued and the per-step loop runs with lane = item.  Four
+//     out of five items never reach it;
 //   * the running minimum distance and the running maximum logits are WARP-SHARED (REDUX after every drain), so a
 //     near agent found by one lane prunes the work of all 32;
 //   * colliding pairs are collected in a team list and their BE bisections (be.py:66-193) are dealt round-robin to
 //     the warps; per-trajectory results are order-independent min/max reductions (lane -> warp REDUX -> team).
 //
 // All bounds are exact (a skipped evaluation cannot change a min / max / threshold decision); results equal the detail
-// kernel's.  Reference semantics: SURVEY.md appendix A; citations on the helpers in fo_metric_dev.cuh.
+// kernel's.  The kernel is instruction-issue- and instruction-cache-bound: code that exists twice after
+// inlining costs more than a flag in a loop, hence the single call sites of the drains and the noinline helpers.  Reference semantics: SURVEY.md appendix A; citations on the helpers in fo_metric_dev.cuh.
 #include <stdlib.h>
 
 #include <mutex>
@@ -154,8 +159,8 @@ struct SweepShape {
 };
 
 // ---------------------------------------------------------------------------------------------
-// UNI: one warp per trajectory and 32 agents per warp pass (the throughput shape): the step index is warp-uniform, so the
-// table rows and the ego state need no per-lane clamping or predication.
+// UNI: one warp per trajectory and 32 agents per warp pass (the throughput shape): window filter + lane = (agent, window)
+// items, no pooled leftovers (see the header comment).
 template <uint32_t MASK, bool STATS, bool UNI>
 __global__ void __launch_bounds__(kSwMaxWarps * 32, FO_SW_MINB)
 fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
