@@ -128,7 +128,9 @@ def test_summary_kernel_matches_oracle(seed, n, a, t, cuda_device):
 
 @pytest.mark.parametrize("seed,n,a,t,metrics", [(35, 300, 32, 31, None), (36, 120, 300, 51, None), (37, 200, 20, 12, None),
                                                 (38, 150, 64, 97, None), (39, 200, 40, 31, ["hr", "cp"]),
-                                                (40, 200, 40, 31, ["dce", "ttc", "wttc"])])
+                                                (40, 200, 40, 31, ["dce", "ttc", "wttc"]),
+                                                (41, 100, 17, 9, None), (42, 100, 33, 8, None), (43, 60, 64, 2, None),
+                                                (44, 40, 32, 128, None)])
 def test_window_filter_shape_matches_oracle(seed, n, a, t, metrics, cuda_device, monkeypatch):
     """One warp per trajectory and >= 17 agents is the throughput shape with the (agent, 8-step window) filter in
     front of the per-step loop; bundles this small normally take the multi-warp shape, so force it."""
@@ -211,6 +213,20 @@ def test_ragged_agent_lengths_summary(cuda_device):
     for detail in (False, True):
         res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
         _check(parity.compare_bundle(out, res, case))
+
+
+def test_ragged_agent_lengths_window_filter(cuda_device, monkeypatch):
+    """The same ragged predictions through the one-warp shape: windows that an agent only partly has, or does not
+    have at all, must neither be evaluated nor hide a step."""
+    monkeypatch.setenv("FO_TEAM_WARPS", "1")
+    case = S.make_case(150, 36, 31, seed=72, agent_states=51)
+    for k, ag in enumerate(case["agents"]):
+        keep = [51, 31, 30, 17, 16, 9, 8, 2, 1][k % 9]
+        for key in ("pos", "yaw", "v", "var"):
+            ag[key] = np.asarray(ag[key])[:keep]
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    _check(parity.compare_bundle(out, res, case))
 
 
 def test_claimed_trajectories_equal_static_striding(cuda_device, monkeypatch):
