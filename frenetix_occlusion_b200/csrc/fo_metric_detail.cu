@@ -90,6 +90,35 @@ __device__ float be_bisect(const MetricKArgs& k, const EgoState (&e)[NP], float 
 }
 
 // ---------------------------------------------------------------------------------------------
+// One copy each of the two big per-state bodies (36 erfcf; atan2f + two angle classes): the kernel evaluates NP
+// register passes per agent and was instruction-cache-bound with them inlined NP times.
+// Collision probability of one gated step, collision_probability.py:94-122: same term order as the reference's loops.
+static __device__ __noinline__ float detail_cp(float mx, float my, float hx, float hy, float bx, float by, float pix,
+                                               float piy, float L6, float W2) {
+  float prob = 0.0f;
+#pragma unroll 1
+  for (int m = 0; m < 3; ++m) {
+    const float ux = (m == 0) ? mx : (m == 1 ? mx + hx : mx - hx);
+    const float uy = (m == 0) ? my : (m == 1 ? my + hy : my - hy);
+#pragma unroll 1
+    for (int b = 0; b < 3; ++b) {
+      const float cxb = (b == 0) ? 0.0f : (b == 1 ? bx : -bx);
+      const float cyb = (b == 0) ? 0.0f : (b == 1 ? by : -by);
+      const float px = half_derf((cxb - L6 - ux) * pix, (cxb + L6 - ux) * pix);
+      const float py = half_derf((cyb - W2 - uy) * piy, (cyb + W2 - uy) * piy);
+      prob = fmaf(px, py, prob);
+    }
+  }
+  return prob * (1.0f / 3.0f);
+}
+
+// LR4S impact-angle coefficients of ego and obstacle (logistic_regression.py:35-48, harm_model.py:81-105)
+static __device__ __noinline__ float2 detail_lr4s_pair(float dyr, float dxr, float th, float psi, float side, float rear) {
+  const float PI_F = 3.14159265358979323846f;
+  const float rel = atan2f(dyr, dxr);
+  return make_float2(lr4s_coef(rel - th, side, rear), lr4s_coef(PI_F + rel - psi, side, rear));
+}
+
 template <int NP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __grid_constant__ MetricKArgs k) {
   __shared__ float sm_be[kWarpsPerCta][4][FO_MAX_STATES];
@@ -173,11 +202,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
         if (do_hr && i < nH) {
           float dv = sqrtf(fmaxf(fmaf(E.v, E.v, s1.y * s1.y) - 2.0f * E.v * s1.y * c, 0.0f));
           if (P.model == 1) {
-            float rel = atan2f(dyr, dxr);
-            float ae = rel - E.th;
-            float ao = PI_F + rel - s1.x;
-            he[p] = logistic_neg(-k.hc.rs_const - k.hc.rs_speed * (P.ke * dv) - lr4s_coef(ae, k.hc.rs_side, k.hc.rs_rear));
-            ho[p] = logistic_neg(-k.hc.rs_const - k.hc.rs_speed * (P.ko * dv) - lr4s_coef(ao, k.hc.rs_side, k.hc.rs_rear));
+            const float2 cls = detail_lr4s_pair(dyr, dxr, E.th, s1.x, k.hc.rs_side, k.hc.rs_rear);
+            he[p] = logistic_neg(-k.hc.rs_const - k.hc.rs_speed * (P.ke * dv) - cls.x);
+            ho[p] = logistic_neg(-k.hc.rs_const - k.hc.rs_speed * (P.ko * dv) - cls.y);
           } else if (P.model == 0) {
             he[p] = logistic_neg(-k.hc.ia_const - k.hc.ia_speed * (P.ke * dv));
             ho[p] = logistic_neg(k.hc.ped_const - k.hc.ped_speed * (P.ko * dv));
@@ -195,22 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fo_metric_kernel(const __gr
           float d1 = fmaf(mx + hx, mx + hx, (my + hy) * (my + hy));
           float d2 = fmaf(mx - hx, mx - hx, (my - hy) * (my - hy));
           if (fminf(d0, fminf(d1, d2)) <= 25.0f) {        // strict "> 5.0" gate, collision_probability.py:65-67
-            float bx = k.L3 * E.c, by = k.L3 * E.s;       // box centre offsets (+-L/3 along theta)
-            float prob = 0.0f;
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-              float ux = (m == 0) ? mx : (m == 1 ? mx + hx : mx - hx);
-              float uy = (m == 0) ? my : (m == 1 ? my + hy : my - hy);
-#pragma unroll
-              for (int b = 0; b < 3; ++b) {
-                float cxb = (b == 0) ? 0.0f : (b == 1 ? bx : -bx);
-                float cyb = (b == 0) ? 0.0f : (b == 1 ? by : -by);
-                float px = half_derf((cxb - k.L6 - ux) * pix, (cxb + k.L6 - ux) * pix);
-                float py = half_derf((cyb - k.W2 - uy) * piy, (cyb + k.W2 - uy) * piy);
-                prob = fmaf(px, py, prob);
-              }
-            }
-            cp[p] = prob * (1.0f / 3.0f);
+            cp[p] = detail_cp(mx, my, hx, hy, k.L3 * E.c, k.L3 * E.s, pix, piy, k.L6, k.W2);
           }
         }
       }
