@@ -509,6 +509,30 @@ def run_stages(dev):
                          "frames_per_s": F / (ms * 1e-3), "ray_edge_tests_per_s": F * R * 4 * O / (ms * 1e-3),
                          "algorithmic_bytes": F * (O * 21 + R * 8 + O), "bound": "fp32 (20 flop per ray x edge test)"}
     del rect, flags, ego, res
+    # ---- detail-output variant of the dense core (per-pair and per-step arrays materialised) ---------
+    from frenetix_occlusion_b200.engine import AgentSet, MetricEngine
+    nd, ad, td = 20000, 64, 51
+    case = S.make_case(nd, ad, td)
+    eng = MetricEngine(case["vehicle"], case["dt"], case["activated_metrics"], case["thresholds"], device=str(dev))
+    eng.set_agents(AgentSet.from_case(case["agents"]))
+    ego_d = torch.from_numpy(case["ego"].astype(np.float32)).to(dev)
+    r = eng.assess(ego_d, want_pair=True, want_step=True)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.assess(ego_d, want_pair=True, want_step=True, out=r)
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    wr = (r.pair.numel() + r.step.numel()) * 4
+    out["detail_kernel"] = {"workload": f"{nd} trajectories x {ad} agents x {td - 1} steps, pair[N,A,12] and step[N,A,T-1,3] written",
+                            "kernel_ms": ms, "evals_per_s": nd * ad * (td - 1) / (ms * 1e-3),
+                            "written_GB_per_s": wr / (ms * 1e-3) / 1e9,
+                            "note": "compute-bound as well: every step needs the exact box distance and harm logits"}
+    del r, ego_d, eng
     # ---- stage 2: constant-velocity rollout of 256 phantom agents x 51 states ----------------------------------
     rng = np.random.default_rng(5)
     x0, y0, v, phi = rng.uniform(-50, 50, 256), rng.uniform(-50, 50, 256), rng.uniform(1, 10, 256), rng.uniform(-3, 3, 256)
