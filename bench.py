@@ -384,11 +384,13 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = min(N_total, 48 * cores if A >= 128 else 1000)
-        v, sec, _ = cpu_oracle_throughput(wl, n_sample, cores)
+        n_sample = min(N_total, 64 * cores if A >= 128 else 1000)
+        reps = 8
+        v, sec, _ = cpu_oracle_throughput(wl, n_sample, cores, steps=reps, warmup=1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sample} trajectories x {A} agents x {T - 1} steps, oracle B (float64 numpy port of the "
-                         f"reference metrics) on {cores} processes, {sec:.1f} s"}
+               "sample": f"{n_sample} trajectories x {A} agents x {T - 1} steps, {reps} timed passes after one warm-up, "
+                         f"oracle B (float64 numpy port of the reference metrics) on {cores} processes, "
+                         f"{sec:.1f} s per pass"}
 
     # ---- p50 latency of the per-planning-step case (C-lat, device resident, one launch) -----------------
     lat = None
