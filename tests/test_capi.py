@@ -55,3 +55,32 @@ def test_engine_refuses_to_run_without_cuda():
     from frenetix_occlusion_b200 import synthetic as S
     with pytest.raises(RuntimeError):
         MetricEngine(S.VEHICLE, 0.1, S.ALL_METRICS, S.DEFAULT_THRESHOLDS)
+
+
+def test_hot_kernels_stay_inside_the_instruction_cache_budget():
+    """The summary and detail kernels are instruction-issue-bound and sit next to the 32 kB L1.5 instruction cache:
+    inlined duplicates showed up as stall_no_inst and cost 25 % (summary, 70 kB -> 47 kB) and 2.6x (detail, 111 kB ->
+    59 kB) -- DESIGN.md section 6.  Guard the code size of the shapes the benchmark and the planner use."""
+    import shutil
+    import subprocess
+    import pytest
+    from frenetix_occlusion_b200 import _lib as L
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True).stdout
+    sizes, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+        elif name and re.match(r"\s+/\*[0-9a-f]+\*/\s+\S", line):
+            sizes[name] = sizes.get(name, 0) + 16
+    def size_of(*parts):
+        hit = [v for k, v in sizes.items() if all(p in k for p in parts)]
+        assert len(hit) == 1, (parts, sorted(sizes))
+        return hit[0]
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1E") <= 52 * 1024     # all 7 metrics, one-warp window-filter shape
+    assert size_of("fo_metric_sweep_kernel", "ILj111ELb0ELb1E") <= 42 * 1024     # default metrics (no BE)
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb0E") <= 62 * 1024     # team shape (latency path)
+    assert size_of("fo_metric_kernel", "ILi1E") <= 50 * 1024                     # detail kernel, T <= 32
+    assert size_of("fo_metric_kernel", "ILi2E") <= 66 * 1024                     # detail kernel, T <= 64
