@@ -69,17 +69,26 @@ class OAPAgent:
         return {"length": self.shape.length * p["size_factor_length_s"], "width": self.shape.width * p["size_factor_width_s"]}
 
     # ---- device calls (the only places the agents touch the C ABI); host float64 arrays come back -------------
+    # The kernels store float32: positions are rolled out RELATIVE to the agent's start (origin = initial position,
+    # subtracted and added back in float64 on the host), so world coordinates of 1e3 .. 1e4 m keep sub-micrometre
+    # resolution instead of the 6e-5 .. 1e-3 m of an absolute float32 coordinate.
     def _rollout_cv(self, pos, velocity, phi, var_factor):
-        ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], self.dt, self.horizon, 0.1, var_factor, device=self.device)
-        torch.cuda.current_stream(torch.device(self.device)).synchronize()
-        return {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
+        org = (float(pos[0]), float(pos[1]))
+        ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], self.dt, self.horizon, 0.1, var_factor, origin=org,
+                        device=self.device)
+        out = {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}   # .cpu() synchronises
+        out["x"] += org[0]
+        out["y"] += org[1]
+        return out
 
     def _rollout_path(self, paths, pos, velocity, var_factor):
         J = len(paths)
+        org = (float(pos[0]), float(pos[1]))
         ro = rollout_path(paths, [pos[0]] * J, [pos[1]] * J, [velocity] * J, self.dt, self.horizon, 3.0, 0.1, var_factor,
-                          device=self.device)
-        torch.cuda.current_stream(torch.device(self.device)).synchronize()
+                          origin=org, device=self.device)
         out = {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
+        out["x"] += org[0]
+        out["y"] += org[1]
         out["sample"] = ro["sample"].cpu().numpy()
         return out
 
@@ -156,9 +165,12 @@ class OAPPedestrianAgent(OAPAgent):
         return float(angle_between_positive(np.array([1, 0]), calc_normal_vector_to_curve(curve, self.initial_position)))
 
     def _create_cr_predictions(self, timestep) -> list:
+        """agent.py:520-536: the covariances are rebuilt for the SLICED position list (create_cov_matrix on
+        pos_list[timestep:]), i.e. the variance restarts at 0.1 -- the first len(slice) entries of the full list."""
         p = self._full_prediction
+        m = len(p["pos_list"][timestep:])
         return [{"orientation_list": p["orientation_list"][timestep:], "v_list": p["v_list"][timestep:],
-                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"], "cov_list": p["cov_list"][timestep:]}]
+                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"], "cov_list": p["cov_list"][:m]}]
 
 
 class OAPVehicleAgent(OAPAgent):
@@ -188,9 +200,11 @@ class OAPVehicleAgent(OAPAgent):
         self.predictions = self._create_cr_predictions(0)
 
     def _create_cr_predictions(self, timestep) -> list:
-        """agent.py:398-426: one prediction per route reference path."""
+        """agent.py:398-426: one prediction per route reference path; covariances restart at 0.1 for the sliced list
+        (create_cov_matrix(pos_list[timestep:]), agent.py:414-416)."""
         return [{"orientation_list": p["orientation_list"][timestep:], "v_list": p["v_list"][timestep:],
-                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"], "cov_list": p["cov_list"][timestep:]}
+                 "pos_list": p["pos_list"][timestep:], "shape": p["shape"],
+                 "cov_list": p["cov_list"][:len(p["pos_list"][timestep:])]}
                 for p in self._all_predictions]
 
     @staticmethod

@@ -1,6 +1,8 @@
 // Host entry points of the dense metric core: agent-table packing and kernel dispatch.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "fo_metric_dev.cuh"
 
 namespace fo {
@@ -123,7 +125,21 @@ extern "C" int fo_agents_pack(const FoAgentsRaw* raw, const FoVehicle* vehicle, 
   return FO_OK;
 }
 
-static int g_num_sms = 0;
+// SM count per device (a process may drive several GPUs, one per planner thread): cached per ordinal, racing
+// first calls store the same value
+static int num_sms_of_current_device(int* out) {
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cache[kMaxDev];
+  int dev = 0;
+  FO_CUDA_TRY(cudaGetDevice(&dev));
+  int n = (dev >= 0 && dev < kMaxDev) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n == 0) {
+    FO_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDev) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  *out = n;
+  return FO_OK;
+}
 static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, void* stream);
 
 extern "C" int fo_metric_bundle(const FoMetricArgs* a, void* stream) { return metric_bundle_impl(a, nullptr, stream); }
@@ -152,11 +168,8 @@ static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, 
     fo::set_error("fo_metric_bundle: 'be' needs 'ttc' (reference raises KeyError, be.py:39)");
     return FO_ERR_INVALID_ARG;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    FO_CUDA_TRY(cudaGetDevice(&dev));
-    FO_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int g_num_sms = 0;
+  { const int rc = num_sms_of_current_device(&g_num_sms); if (rc != FO_OK) return rc; }
   fo::MetricKArgs k;
   k.ego = a->ego; k.N = a->n_traj; k.T = a->n_states; k.A = a->n_agents; k.Tp = a->t_stride;
   k.tab = fo::agent_table_view(a->agent_table, a->n_agents, a->t_stride);

@@ -87,12 +87,41 @@ __device__ __forceinline__ double pt_box_d2_f64(double px, double py, double hx,
   return dx * dx + dy * dy;
 }
 
+// sin / cos in float64 of a float32 angle.  CUDA's sincos(double) drags an 8 kB Payne-Hanek slow path into every
+// kernel that calls it (the metric kernels live next to a 32 kB instruction cache); headings are float32 values of
+// moderate size, so a two-term Cody-Waite reduction by pi/2 plus the fdlibm kernel polynomials (|r| <= pi/4, error
+// below 1e-16) is exact enough for a tie-break that only matters within 1e-12 of a rounding boundary.
+static __device__ __noinline__ void sincos_f64_of_f32(float af, double* sn, double* cs) {
+  const double a = (double)af;
+  const double q = rint(a * 0.63661977236758134308);                 // 2 / pi
+  double r = fma(-q, 1.57079632679489655800e+00, a);                 // pi/2 high part
+  r = fma(-q, 6.12323399573676603587e-17, r);                        // pi/2 low part
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int n = (int)(long long)q & 3;
+  *sn = (n == 0) ? s : (n == 1) ? c : (n == 2) ? -s : -c;
+  *cs = (n == 0) ? c : (n == 1) ? -s : (n == 2) ? -c : s;
+}
+
 // ego reference point (ex, ey, eth), rectangle centre wb ahead; agent rectangle (ax, ay, ayaw); returns round(d * 1000)
 static __device__ __noinline__ uint32_t obb_round_mm_f64(float ex, float ey, float eth, float wb, float hEx, float hEy,
                                                          float ax, float ay, float ayaw, float hl, float hw) {
   double se, ce, sa, ca;
-  sincos((double)eth, &se, &ce);
-  sincos((double)ayaw, &sa, &ca);
+  sincos_f64_of_f32(eth, &se, &ce);
+  sincos_f64_of_f32(ayaw, &sa, &ca);
   const double cx = (double)ex + (double)wb * ce, cy = (double)ey + (double)wb * se;
   const double rx = (double)ax - cx, ry = (double)ay - cy;
   const double HEx = hEx, HEy = hEy, HL = hl, HW = hw;

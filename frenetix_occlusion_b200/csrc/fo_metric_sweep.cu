@@ -33,6 +33,7 @@
 // inlining costs more than a flag in a loop, hence the single call sites of the drains and the noinline helpers.  Reference semantics: SURVEY.md appendix A; citations on the helpers in fo_metric_dev.cuh.
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "fo_metric_dev.cuh"
@@ -287,6 +288,13 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
             const float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
             const float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, __int_as_float(pa.z), __int_as_float(pa.w)));
             r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);
+            // np.round(d, 3) next to a x.xxx5 boundary: a candidate for the minimum is re-rounded from a float64
+            // evaluation, exactly as in the detail kernel (rmin only falls, so "r <= rmin + 2" is a superset of the
+            // candidates of the final minimum) -- min_dce, wttc and the dce / ttc threshold clauses are then the
+            // float64 reference's except for distances within 1e-12 of a boundary
+            if (near_rounding_boundary(d) && r <= rmin + 2u)
+              r = obb_round_mm_f64(EA.x, EA.y, w.egoB[ii].x, k.wb, k.hEx, k.hEy, s0.x, s0.y,
+                                   __ldg(&k.tab.s1[(size_t)a * k.Tp + ii]).x, __int_as_float(pa.z), __int_as_float(pa.w));
             if (r == 0u) atomicMin(&w.colfirst[ial], (uint32_t)ii);
             if (STATS) ++st_obb;
           }
@@ -721,11 +729,15 @@ static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st)
 template <uint32_t MASK, bool STATS, bool UNI>
 static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st) {
   const size_t smem = sweep_smem_bytes(k.T, W);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // the opt-in shared-memory size is a per-device function attribute: remember what each device has been given
+  static std::atomic<size_t> configured[kMaxDev];
+  int dev = 0;
+  FO_CUDA_TRY(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < kMaxDev;
+  if (!tracked || smem > configured[dev].load(std::memory_order_acquire)) {
     FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    configured = smem;
+    if (tracked) configured[dev].store(smem, std::memory_order_release);
   }
   int per_sm = 1;
   FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS, UNI>, W * 32, smem));

@@ -22,8 +22,11 @@ class Metric:
         self.vehicle_params = vehicle_params
         self.agent_manager = agent_manager
         names = self._check_required_metrics(self.config["activated_metrics"])
+        # ONE source for the harm coefficients: the JSON the HR plugin loads (hr.py:20-24) also feeds the kernel
+        from ..engine import harm_from_reference_json
         self._core = MetricCore(vehicle_params, agent_manager, activated_metrics=[n for n in names],
-                                thresholds=self.metric_thresholds, device=device)
+                                thresholds=self.metric_thresholds, device=device,
+                                harm_coeffs=harm_from_reference_json(HR._load_param("harm_coefficients")))
         self.metrics = self._initialize_metrics(names)
 
     # ---- per trajectory (reference metric.py:35-100) ---------------------------------------------
@@ -31,8 +34,12 @@ class Metric:
         results = {}
         if not self.agent_manager.phantom_agents or not self.metrics:
             return results, True
-        for name, metric in self.metrics.items():
-            results[name] = metric.evaluate(trajectory, results)
+        self._core.begin(trajectory)             # the plugins of this call share one launch; nothing older is reused
+        try:
+            for name, metric in self.metrics.items():
+                results[name] = metric.evaluate(trajectory, results)
+        finally:
+            self._core.end()
 
         thr = self.metric_thresholds
         safety_check = True
@@ -70,6 +77,13 @@ class Metric:
         if not isinstance(trajectories, (np.ndarray, torch.Tensor)):
             trajectories = np.stack([trajectory_to_array(t) for t in trajectories])
         return self._core.bundle(trajectories, want_pair=want_pair, want_step=want_step)
+
+    def prefetch(self, trajectories):
+        """Evaluate all candidates of this planning cycle in one launch; the ``evaluate_metrics`` calls that follow are
+        served from the host copy (see ``MetricCore.prefetch``)."""
+        if not self.agent_manager.phantom_agents or not self.metrics:
+            return 0
+        return self._core.prefetch(trajectories)
 
     def register(self, name, metric, position=None):
         """Plug in a user metric: any object with ``evaluate(trajectory, results)``."""

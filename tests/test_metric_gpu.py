@@ -345,3 +345,51 @@ def test_full_size_sweep_properties(cuda_device):
     res = {"valid": v0.cpu().numpy()[idx], "summary": s0.cpu().numpy()[idx], "flags": f0.cpu().numpy()[idx].astype(np.uint32),
            "pair": None, "step": None}
     _check(parity.compare_bundle(out, res, sub))
+
+
+def test_per_trajectory_results_are_never_reused_across_trajectories(cuda_device):
+    """Regression: the per-trajectory result cache must not key on id() of freed objects.  Freshly built trajectory
+    objects that are dropped right after their call (CPython then reuses their addresses) and whose ``cartesian.x``
+    is a new array per access (pybind-style) must each get their own results; an in-place edit must be seen too."""
+    import types
+    from frenetix_occlusion_b200.metrics.metric import Metric
+    case = S.make_case(24, 6, 31, seed=21)
+    out = MO.evaluate_bundle(case)
+    am = _agent_manager_from_case(case)
+    vp = types.SimpleNamespace(**case["vehicle"])
+    metric = Metric({"activated_metrics": list(case["activated_metrics"]), "metric_thresholds": dict(case["thresholds"])}, vp, am)
+
+    class Cart:
+        def __init__(self, arr):
+            self._a = arr
+        x = property(lambda self: np.array(self._a[:, 0]))
+        y = property(lambda self: np.array(self._a[:, 1]))
+        theta = property(lambda self: np.array(self._a[:, 2]))
+        v = property(lambda self: np.array(self._a[:, 3]))
+        a = property(lambda self: np.array(self._a[:, 4]))
+
+    pids = list(am.predictions.keys())
+    for n in range(24):
+        tr = types.SimpleNamespace(cartesian=Cart(np.asarray(case["ego"][n], dtype=np.float64)))
+        results, ok = metric.evaluate_metrics(tr)
+        got = np.array([results["dce"][p]["dce"] for p in pids])
+        assert np.array_equal(got, out["dce"][n]), n
+        assert ok == bool(out["valid"][n])
+        del tr, results
+    # in-place mutation of one object between two calls
+    arr = np.array(case["ego"][0], dtype=np.float64)
+    tr = types.SimpleNamespace(cartesian=Cart(arr))
+    r0, _ = metric.evaluate_metrics(tr)
+    arr[:] = case["ego"][5]
+    r1, _ = metric.evaluate_metrics(tr)
+    assert np.array_equal(np.array([r1["dce"][p]["dce"] for p in pids]), out["dce"][5])
+    # prefetch: one launch for all candidates, the per-trajectory calls answer from the host copy with equal dicts
+    trs = [types.SimpleNamespace(cartesian=Cart(np.asarray(case["ego"][n], dtype=np.float64))) for n in range(24)]
+    direct = [metric.evaluate_metrics(t) for t in trs]
+    from frenetix_occlusion_b200 import _lib as L
+    metric.prefetch(trs)
+    l0 = L.lib.fo_launch_count()
+    served = [metric.evaluate_metrics(t) for t in trs]
+    assert L.lib.fo_launch_count() == l0, "prefetched trajectories must not launch again"
+    for (ra, oka), (rb, okb) in zip(direct, served):
+        assert oka == okb and not compare_results(ra, rb, rtol=0, atol=0)

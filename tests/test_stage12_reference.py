@@ -129,3 +129,34 @@ def test_cuda_agent_manager_equals_reference(gold, cuda_device):
     assert [int(st[0].time_step), int(st[-1].time_step)] == g["time_steps"]
     np.testing.assert_allclose(st[0].position, g["first"], atol=4e-6)
     np.testing.assert_allclose(st[-1].position, g["last"], atol=4e-6)
+    # update_real_agents (agent.py:171-177, 520-534): the sliced prediction gets covariances REBUILT for the slice
+    # (create_cov_matrix(pos_list[timestep:])), i.e. the variance restarts at 0.1 instead of continuing at 0.1 * vf^t
+    real = am.real_agents[-1]
+    am.timestep = 20
+    preds = {real.agent_id: None}
+    am.update_real_agents(preds)
+    q = preds[real.agent_id]
+    n = len(q["pos_list"])
+    assert n == 51 - 20 and len(q["cov_list"]) == n and len(q["v_list"]) == n
+    vf = R.deployment_config()["agent_manager"]["prediction"]["variance_factor"]
+    np.testing.assert_allclose(np.asarray(q["cov_list"])[:, 0, 0], 0.1 * vf ** np.arange(n), rtol=1e-6)
+    np.testing.assert_allclose(q["pos_list"][0], real._full_prediction["pos_list"][20], atol=0)
+
+
+@pytest.mark.gpu
+def test_rollouts_keep_float64_resolution_far_from_the_origin(cuda_device):
+    """Predictions are rolled out relative to the agent's start and shifted back in float64: at world coordinates of
+    1e4 m an absolute float32 position would be off by up to 1e-3 m (the rounding grid of np.round(dce, 3))."""
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.agent import FOAgentManager
+    sc = _scene()
+    ego = R.OpenLoopEgo(sc)
+    random.seed(3)
+    am = FOAgentManager(scenario=sc, reference_path=ego.reference_path, config=R.deployment_config()["agent_manager"],
+                        timestep=0, dt=sc.dt)
+    p0 = np.array([12345.678901, -9876.543211])
+    am.add_agent(pos=p0, velocity=1.4, agent_type="Pedestrian", timestep=0, horizon=3.0, orientation=0.7)
+    q = list(am.predictions.values())[0]
+    exp = VO.rollout_cv(p0[0], p0[1], 1.4, 0.7, sc.dt, 3.0)
+    np.testing.assert_allclose(q["pos_list"], np.column_stack((exp["x"][0], exp["y"][0])), rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(q["pos_list"][0], p0)
