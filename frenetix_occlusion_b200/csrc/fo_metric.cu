@@ -1,4 +1,5 @@
 // Host entry points of the dense metric core: agent-table packing and kernel dispatch.
+#include <math.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -29,15 +30,35 @@ __device__ __forceinline__ int protection_model(int kind) {  // harm_model.py:15
   }
 }
 
+// Slot order: stable sort by harm model.  One CTA; A is a few hundred at most, so the O(A^2) rank count is free.
+__global__ void fo_agents_order_kernel(const int32_t* __restrict__ kind, int A, int Ap, int32_t* orig, int32_t* slot) {
+  for (int a = threadIdx.x; a < Ap; a += blockDim.x) {
+    if (a >= A) { orig[a] = -1; slot[a] = a; continue; }      // padding slots keep their place behind the real ones
+#ifdef FO_NO_SORT
+    slot[a] = a; orig[a] = a; continue;
+#endif
+    const int m = protection_model(kind[a]);
+    int rank = 0;
+    for (int b = 0; b < A; ++b) {
+      const int mb = protection_model(kind[b]);
+      rank += (mb < m) | ((mb == m) & (b < a));
+    }
+    slot[a] = rank;
+    orig[rank] = a;
+  }
+}
+
 __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, float4* s1, float2* s2, AgentParams* prm,
-                                      float4* t0, float* tv, float4* aw, float* avw, int Ap) {
+                                      float4* t0, float* tv, float* tpsi, float4* aw, float* avw,
+                                      const int32_t* __restrict__ orig, const int32_t* __restrict__ slot, int Ap) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int A = raw.n_agents, Tp = raw.t_stride;
   const int nW = agent_windows(Tp);
-  if (idx < Ap * nW) {                       // window boxes for the summary kernel's filter
-    const int a = idx / nW, wi = idx - a * nW;
+  if (idx < Ap * nW) {                       // window boxes for the summary kernel's filter (slot order)
+    const int sl = idx / nW, wi = idx - sl * nW;
     float xl = 1e30f, xh = -1e30f, yl = 1e30f, yh = -1e30f, vm = 0.0f;
-    if (a < A) {
+    if (sl < A) {
+      const int a = orig[sl];
       const int nS = min(raw.n_states[a], Tp);
       const int lo = wi * kWinSteps;
       for (int i = max(lo - 1, 0); i < min(lo + kWinSteps, nS); ++i) {
@@ -46,16 +67,18 @@ __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, 
         if (i >= lo) vm = fmaxf(vm, fabsf(raw.v[a * Tp + i]));
       }
     }
-    aw[(size_t)wi * Ap + a] = make_float4(xl, xh, yl, yh);
-    avw[(size_t)wi * Ap + a] = vm;
+    aw[(size_t)wi * Ap + sl] = make_float4(xl, xh, yl, yh);
+    avw[(size_t)wi * Ap + sl] = vm;
   }
-  if (idx >= A * Tp && idx < Ap * Tp) {      // padding agents of the time-major copy
-    const int a = idx / Tp, i = idx - a * Tp;
-    t0[(size_t)i * Ap + a] = make_float4(0, 0, 1, 0);
-    tv[(size_t)i * Ap + a] = 0.0f;
+  if (idx >= A * Tp && idx < Ap * Tp) {      // padding slots of the time-major copies
+    const int sl = idx / Tp, i = idx - sl * Tp;
+    t0[(size_t)i * Ap + sl] = make_float4(0, 0, 1, 0);
+    tv[(size_t)i * Ap + sl] = 0.0f;
+    tpsi[(size_t)i * Ap + sl] = 0.0f;
   }
   if (idx < A * Tp) {
     const int a = idx / Tp, i = idx - a * Tp;
+    const int sl = slot[a];
     float4 o0 = make_float4(0, 0, 1, 0), o1 = make_float4(0, 0, 0, 0);
     float2 o2 = make_float2(1, 1);
     if (i < raw.n_states[a]) {
@@ -69,11 +92,13 @@ __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, 
       o1 = make_float4(yaw, raw.v[idx], raw.x[ip], raw.y[ip]);
       o2 = make_float2(rsqrtf(2.0f * vx), rsqrtf(2.0f * vy));
     }
-    s0[idx] = o0;
-    s1[idx] = o1;
-    s2[idx] = o2;
-    t0[(size_t)i * Ap + a] = o0;
-    tv[(size_t)i * Ap + a] = o1.y;
+    const size_t am = (size_t)sl * Tp + i, tm = (size_t)i * Ap + sl;
+    s0[am] = o0;
+    s1[am] = o1;
+    s2[am] = o2;
+    t0[tm] = o0;
+    tv[tm] = o1.y;
+    tpsi[tm] = o1.x;
   }
   if (idx < A) {
     AgentParams p;
@@ -86,7 +111,7 @@ __global__ void fo_agents_pack_kernel(FoAgentsRaw raw, float m_ego, float4* s0, 
     p.ke = mo / (m_ego + mo);
     p.ko = m_ego / (m_ego + mo);
     p.pad = sqrtf(p.hl * p.hl + p.hw * p.hw);   // circumradius of the unbuffered rectangle (distance lower bound)
-    prm[idx] = p;
+    prm[slot[idx]] = p;
   }
 }
 
@@ -116,11 +141,13 @@ extern "C" int fo_agents_pack(const FoAgentsRaw* raw, const FoVehicle* vehicle, 
   }
   fo::AgentTableView v = fo::agent_table_view(table_dev, A, Tp);
   const int total = v.Ap * Tp;
+  fo::fo_agents_order_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(raw->kind, A, v.Ap, const_cast<int32_t*>(v.orig),
+                                                                  const_cast<int32_t*>(v.slot));
   fo::fo_agents_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       *raw, vehicle->mass, const_cast<float4*>(v.s0), const_cast<float4*>(v.s1), const_cast<float2*>(v.s2),
       const_cast<fo::AgentParams*>(v.prm), const_cast<float4*>(v.t0), const_cast<float*>(v.tv),
-      const_cast<float4*>(v.aw), const_cast<float*>(v.avw), v.Ap);
-  fo::count_launch();
+      const_cast<float*>(v.tpsi), const_cast<float4*>(v.aw), const_cast<float*>(v.avw), v.orig, v.slot, v.Ap);
+  fo::count_launch(2);
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;
 }
@@ -180,8 +207,22 @@ static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, 
   k.mmask = a->metric_mask; k.tmask = a->threshold_mask;
   k.thr_harm = a->thr_harm; k.thr_risk = a->thr_risk; k.thr_be = a->thr_be; k.thr_cp = a->thr_cp;
   k.thr_ttc = a->thr_ttc; k.thr_dce = a->thr_dce;
+  {
+    // smallest r with r / 1000.0 >= thr_dce (the reference compares np.round(d, 3) = r / 1000.0 in float64)
+    long long c = (long long)ceil(a->thr_dce * 1000.0);
+    if (!(a->thr_dce > 0.0)) c = 0;
+    if (c > 0xffffff) c = 0xffffff;
+    while (c > 0 && (double)(c - 1) / 1000.0 >= a->thr_dce) --c;
+    while (c < 0xffffff && (double)c / 1000.0 < a->thr_dce) ++c;
+    k.thr_dce_mm = (uint32_t)c;
+    // smallest step with np.round(step * dt, 3) >= thr_ttc
+    uint32_t q = 0;
+    while (q < (uint32_t)FO_MAX_STATES + 1u && rint((double)q * a->dt * 1000.0) / 1000.0 < a->thr_ttc) ++q;
+    k.thr_ttc_col = q;
+  }
   k.valid = a->valid; k.summary = a->summary; k.flags = a->flags; k.pair = a->pair; k.step = a->step;
   k.stats = stats;
+  { const char* e = getenv("FO_EXACT_DCE"); k.exact_dce = e && e[0] == '1'; }
   k.claim = nullptr;
 
   cudaStream_t st = (cudaStream_t)stream;

@@ -23,6 +23,11 @@ struct MetricKArgs {
   double dtd;
   uint32_t mmask, tmask;
   double thr_harm, thr_risk, thr_be, thr_cp, thr_ttc, thr_dce;
+  // the two discrete threshold clauses in the units the kernels hold (host-computed, exact in float64):
+  //   dce < thr_dce   <=>  round(d * 1000) < thr_dce_mm        (np.round(d, 3) = r / 1000.0, dce.py:79, metric.py:92-98)
+  //   ttc < thr_ttc   <=>  first colliding step < thr_ttc_col  (np.round(step * dt, 3), ttc.py:43, metric.py:85-89)
+  uint32_t thr_dce_mm, thr_ttc_col;
+  bool exact_dce;      // summary kernel: re-round np.round(d, 3) ties in float64 even when no threshold needs it (FO_EXACT_DCE=1)
   uint8_t* valid;
   float* summary;
   uint32_t* flags;
@@ -33,6 +38,20 @@ struct MetricKArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ AgentParams load_params(const AgentParams* p) {   // two 16-byte loads
+  const int4* q = reinterpret_cast<const int4*>(p);
+  int4 a = __ldg(q), b = __ldg(q + 1);
+  AgentParams r;
+  r.n_states = a.x; r.model = a.y; r.hl = __int_as_float(a.z); r.hw = __int_as_float(a.w);
+  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = __int_as_float(b.w);
+  return r;
+}
+
+// r / 1000 as the float the outputs carry (r = round(d * 1000) is exact in float32; correctly rounded division)
+__device__ __forceinline__ float mm_to_m(uint32_t r) { return __fdiv_rn((float)r, 1000.0f); }
+// np.round(step * dt, 3) as a float (ttc.py:43)
+__device__ __forceinline__ float step_to_s(uint32_t step, double dt) { return (float)(rint((double)step * dt * 1000.0) * 0.001); }
+
 __device__ __forceinline__ float umaxf(float v) {  // warp max of non-negative floats (bit order == value order)
   return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
 }
@@ -181,8 +200,11 @@ __device__ __forceinline__ float erfc_pos_fast(float z) {
 // Collision probability of one gated step (collision_probability.py:94-122): Gaussian mass of the 3 obstacle
 // points over the 3 axis-aligned ego boxes, divided by 3.  (mx, my) = obstacle position i-1 minus ego position i,
 // (hx, hy) = half buffered length along yaw_i, (bx, by) = (L/3)(cos, sin theta_i), s2 = 1/(sqrt2 sigma_{x,y}).
-// A factor whose standardised interval lies beyond 4.7 (erfc < 3e-11) contributes less than the 1e-10 that the
-// comparison floor of 2e-7 can resolve and is skipped before any erfc is evaluated.
+// CUT (summary kernel): a factor whose standardised interval lies beyond 4.7 (erfc < 3e-11) contributes less than the
+// 1e-10 that the comparison floor of 2e-7 can resolve and is skipped before any erfc is evaluated.  The detail kernel
+// evaluates all nine terms: its per-step values feed first-index decisions of the reference's result dict
+// (max_obst_risk_index = first maximum of harm x cp, hr.py:87-98), where a 1e-12 must not become an exact zero.
+template <bool CUT = true>
 __device__ __forceinline__ float cp_gauss_boxes(float mx, float my, float hx, float hy, float bx, float by, float2 s2,
                                                 float L6, float W2) {
   constexpr float kFar = 4.7f;
@@ -194,10 +216,10 @@ __device__ __forceinline__ float cp_gauss_boxes(float mx, float my, float hx, fl
     const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
     const float uy = fmaf(fm, hy, my), cyb = fb * by;
     const float ya = (cyb - W2 - uy) * s2.y, yb = (cyb + W2 - uy) * s2.y;     // ya < yb
-    if (ya > kFar || yb < -kFar) continue;
+    if (CUT && (ya > kFar || yb < -kFar)) continue;
     const float ux = fmaf(fm, hx, mx), cxb = fb * bx;
     const float xa = (cxb - L6 - ux) * s2.x, xb = (cxb + L6 - ux) * s2.x;
-    if (xa > kFar || xb < -kFar) continue;
+    if (CUT && (xa > kFar || xb < -kFar)) continue;
     const float eya = erfc_pos_fast(fabsf(ya)), eyb = erfc_pos_fast(fabsf(yb));
     const float py = ((ya > 0.0f) == (yb > 0.0f)) ? fabsf(eya - eyb) : (2.0f - eya - eyb);
     const float exa = erfc_pos_fast(fabsf(xa)), exb = erfc_pos_fast(fabsf(xb));
@@ -336,6 +358,8 @@ struct EgoState {
 };
 
 
+// one zeroed-per-launch device counter (trajectory claims of the persistent kernels), see fo_metric_sweep.cu
+unsigned int* claim_slot(cudaStream_t st);
 int launch_metric_detail(const MetricKArgs& k, int num_sms, cudaStream_t st);
 int launch_metric_sweep(const MetricKArgs& k, int num_sms, cudaStream_t st);
 

@@ -58,7 +58,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int T, int W) {
   size_t b = (size_t)kSwTile * (8 + 4 + 2)       // pairkey, colfirst, BE pair list
              + 8 * 4 + kSwInvBytes               // scalars, arc-length bucket table
              + (size_t)kSwWinQueue * 2           // (agent, window) work items of the window filter
-             + (size_t)W * 2 * kSwQueue * 4      // per-warp near / cp queues
+             + (size_t)W * 3 * kSwQueue * 4      // per-warp near / cp / rounding-tie queues
              + (size_t)W * 2 * 32 * 4            // pooled leftovers
              + (size_t)W * 16 * 4                // per-warp partial results
              + nW * 16                           // ego window boxes
@@ -76,6 +76,7 @@ struct SweepSmem {
   uint32_t* colfirst;           // [kSwTile] first step with rounded distance 0
   uint32_t* q_near;             // [W][kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
   uint32_t* q_cp;               // [W][kSwQueue] (agent-in-tile << 8 | step)
+  uint32_t* q_tie;              // [W][kSwQueue] (agent-in-tile << 8 | step): distances to re-round in float64
   uint32_t* pool_near;          // [W * 32] leftovers of all warps
   uint32_t* pool_cp;            // [W * 32]
   float* red;                   // [W][16]
@@ -99,7 +100,8 @@ __device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int 
   w.q_win = reinterpret_cast<uint16_t*>(w.inv + kSwInvBytes);
   w.q_near = reinterpret_cast<uint32_t*>(w.q_win + kSwWinQueue);
   w.q_cp = w.q_near + (size_t)W * kSwQueue;
-  w.pool_near = w.q_cp + (size_t)W * kSwQueue;
+  w.q_tie = w.q_cp + (size_t)W * kSwQueue;
+  w.pool_near = w.q_tie + (size_t)W * kSwQueue;
   w.pool_cp = w.pool_near + (size_t)W * 32;
   w.red = reinterpret_cast<float*>(w.pool_cp + (size_t)W * 32);
   w.ew = reinterpret_cast<float4*>(w.red + (size_t)W * 16);
@@ -108,15 +110,6 @@ __device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int 
   w.dist = reinterpret_cast<float*>(w.egoB + T);
   w.evw = w.dist + ((T + 3) & ~3);
   return w;
-}
-
-__device__ __forceinline__ AgentParams sw_load_params(const AgentParams* p) {
-  const int4* q = reinterpret_cast<const int4*>(p);
-  int4 a = __ldg(q), b = __ldg(q + 1);
-  AgentParams r;
-  r.n_states = a.x; r.model = a.y; r.hl = __int_as_float(a.z); r.hw = __int_as_float(a.w);
-  r.hlb = __int_as_float(b.x); r.ke = __int_as_float(b.y); r.ko = __int_as_float(b.z); r.pad = __int_as_float(b.w);
-  return r;
 }
 
 // order-preserving float <-> uint map (warp max of signed floats with one REDUX)
@@ -155,6 +148,26 @@ __device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, 
   }
 }
 
+// np.round(d, 3) next to a x.xxx5 boundary (dce.py:79): queued candidates for the minimum are re-rounded from a float64
+// evaluation, 32 at a time with all lanes busy and out of line -- the float64 code (6 kB) and its call stay off the hot
+// path of the drains.  Returns the minimum of the re-rounded values; steps that round to 0 enter colfirst.
+static __device__ __noinline__ uint32_t sw_drain_ties(const MetricKArgs& k, const float4* egoA, const float2* egoB,
+                                                      uint32_t* colfirst, const uint32_t* src, int cnt, int a0, int lane) {
+  uint32_t r = 0xffffffu;
+  if (lane < cnt) {
+    const uint32_t item = src[lane];
+    const int ial = (int)(item >> 8), ii = (int)(item & 0xffu);
+    const int a = a0 + ial;
+    const float4 s0 = __ldg(&k.tab.t0[(size_t)ii * k.tab.Ap + a]);
+    const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
+    const float4 EA = egoA[ii];
+    r = obb_round_mm_f64(EA.x, EA.y, egoB[ii].x, k.wb, k.hEx, k.hEy, s0.x, s0.y,
+                         __ldg(&k.tab.s1[(size_t)a * k.Tp + ii]).x, __int_as_float(pa.z), __int_as_float(pa.w));
+    if (r == 0u) atomicMin(&colfirst[ial], (uint32_t)ii);
+  }
+  return __reduce_min_sync(kFull, r);
+}
+
 struct SweepShape {
   int lg_agents;   // log2 of the agents held by one warp (0..5); a warp has 32 >> lg_agents time slices
 };
@@ -162,7 +175,7 @@ struct SweepShape {
 // ---------------------------------------------------------------------------------------------
 // UNI: one warp per trajectory and 32 agents per warp pass (the throughput shape): window filter + lane = (agent, window)
 // items, no pooled leftovers (see the header comment).
-template <uint32_t MASK, bool STATS, bool UNI>
+template <uint32_t MASK, bool STATS, bool UNI, bool TIES>
 __global__ void __launch_bounds__(kSwMaxWarps * 32, FO_SW_MINB)
 fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,6 +185,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const SweepSmem w = sweep_smem(smem_raw, T, UNI ? 1 : W);
   uint32_t* const q_near = w.q_near + wib * kSwQueue;
   uint32_t* const q_cp = w.q_cp + wib * kSwQueue;
+  uint32_t* const q_tie = w.q_tie + wib * kSwQueue;
   const uint32_t mm = MASK ? MASK : k.mmask;
   const bool do_cp = mm & FO_M_CP, do_dce = mm & FO_M_DCE, do_hr = mm & FO_M_HR, do_be = mm & FO_M_BE,
              do_ttc = mm & FO_M_TTC;
@@ -243,7 +257,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       const int nAt = min(kSwTile, k.A - a0);
       for (int j = tid; j < nAt; j += nthr) { w.pairkey[j] = 0ull; w.colfirst[j] = 0xffffffffu; }
       __syncthreads();                                 // ego staged, pair arrays cleared
-      int qn = 0, qc = 0;
+      int qn = 0, qc = 0, qt = 0;
       // per-lane bound state of the current lane group (refreshed after every drain)
       float lim0 = 0.0f, lim2 = 0.0f, thr2 = CUDART_INF_F;
       float kse = 0.0f, kso = 0.0f, kce = 0.0f, kco = 0.0f;
@@ -275,6 +289,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (lane < cnt) item = src[lane];
         __syncwarp();
         uint32_t r = 0xffffffu;
+        bool tie = false;
         if (lane < cnt) {
           const int ial = (int)((item >> 8) & 0xffffu), ii = (int)(item & 0xffu);
           const int a = a0 + ial;
@@ -288,14 +303,15 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
             const float rx = fmaf(dx, EA.z, dy * EA.w), ry = fmaf(dy, EA.z, -dx * EA.w);
             const float d = sqrtf(obb_d2(rx, ry, c, s, k.hEx, k.hEy, __int_as_float(pa.z), __int_as_float(pa.w)));
             r = (uint32_t)__float2int_rn(fminf(d, 8000.0f) * 1000.0f);
-            // np.round(d, 3) next to a x.xxx5 boundary: a candidate for the minimum is re-rounded from a float64
-            // evaluation, exactly as in the detail kernel (rmin only falls, so "r <= rmin + 2" is a superset of the
-            // candidates of the final minimum) -- min_dce, wttc and the dce / ttc threshold clauses are then the
-            // float64 reference's except for distances within 1e-12 of a boundary
-            if (near_rounding_boundary(d) && r <= rmin + 2u)
-              r = obb_round_mm_f64(EA.x, EA.y, w.egoB[ii].x, k.wb, k.hEx, k.hEy, s0.x, s0.y,
-                                   __ldg(&k.tab.s1[(size_t)a * k.Tp + ii]).x, __int_as_float(pa.z), __int_as_float(pa.w));
-            if (r == 0u) atomicMin(&w.colfirst[ial], (uint32_t)ii);
+            // np.round(d, 3) next to a x.xxx5 boundary: a candidate for the minimum is queued for a float64
+            // re-rounding (rmin only falls, so "r <= rmin + 2" is a superset of the candidates of the final minimum);
+            // until then it bounds the minimum from above with r + 1 -- min_dce, wttc and the dce / ttc threshold
+            // clauses are then the float64 reference's except for distances within 1e-12 of a boundary
+            if (TIES) {
+              tie = near_rounding_boundary(d) && r <= rmin + 2u;
+              if (tie) ++r;
+            }
+            if (r == 0u && !tie) atomicMin(&w.colfirst[ial], (uint32_t)ii);
             if (STATS) ++st_obb;
           }
           if (item & 0x80000000u) {            // LR4S logits with the impact-angle class (protected agents)
@@ -312,6 +328,15 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           }
         }
         rmin = min(rmin, __reduce_min_sync(kFull, r));
+        if (TIES) {
+          const unsigned tb = __ballot_sync(kFull, tie);
+          if (tb) {
+            if (tie) q_tie[qt + __popc(tb & lt_mask)] = item & 0xffffffu;
+            qt += __popc(tb);
+            __syncwarp();
+            if (qt >= 32) { qt -= 32; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, 32, a0, lane)); }
+          }
+        }
         zb_e = fmaxf(zb_e, warp_max_signed(acc_ze));
         zb_o = fmaxf(zb_o, warp_max_signed(acc_zo));
         upd_lim();
@@ -324,7 +349,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (lane < cnt) {
           const int ial = (int)(item >> 8), ii = (int)(item & 0xffu), t = ii - 1;
           const int a = a0 + ial;
-          const AgentParams P = sw_load_params(k.tab.prm + a);
+          const AgentParams P = load_params(k.tab.prm + a);
           const size_t idx = (size_t)a * k.Tp + ii;
           const float4 s0i = __ldg(&k.tab.s0[idx]);
           const float4 s1i = __ldg(&k.tab.s1[idx]);
@@ -359,7 +384,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const int a = a0 + al;
         AgentParams P;
         P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
-        if (alive) P = sw_load_params(k.tab.prm + a);
+        if (alive) P = load_params(k.tab.prm + a);
         const int nS = min(P.n_states, i_hi);             // this lane evaluates steps [i_lo, nS)
         const int nH = min(nS, T - 1);                    // harm is evaluated at steps < min(T-1, n_states)
         const int n_it = flush ? 1 : (int)__reduce_max_sync(kFull, (unsigned)max(nS - i_lo, 0));
@@ -462,7 +487,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
             if (stale) {
               AgentParams P;
               P.n_states = 0; P.model = 2; P.hl = P.hw = P.hlb = P.ke = P.ko = P.pad = 0.0f;
-              if (al < nAt) P = sw_load_params(k.tab.prm + a0 + al);
+              if (al < nAt) P = load_params(k.tab.prm + a0 + al);
               f_nS = min(P.n_states, T);
               f_nH = min(f_nS, T - 1);
               f_nW = (int)__reduce_max_sync(kFull, (unsigned)((f_nS + kWinSteps - 1) / kWinSteps));
@@ -527,6 +552,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       }
       // ---- pool what is left in the per-warp queues across the team and drain it cooperatively --------------
       is_m1 = false;
+      if (TIES && UNI && qt > 0) { rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie, qt, a0, lane)); qt = 0; }
       if (!UNI) {
         unsigned base_n = 0, base_c = 0;
         if (lane == 0) {
@@ -541,6 +567,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const int tot_n = (int)w.scal[2], tot_c = (int)w.scal[3];
         for (int c = wib * 32; c < tot_n; c += 32 * W) drain_near(w.pool_near + c, min(32, tot_n - c));
         for (int c = wib * 32; c < tot_c; c += 32 * W) drain_cp(w.pool_cp + c, min(32, tot_c - c));
+        while (TIES && qt > 0) { const int c = min(qt, 32); qt -= c; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, c, a0, lane)); }
       }
       __syncthreads();                                 // pairkey / colfirst of the tile complete
       if (tid == 0) { w.scal[2] = 0u; w.scal[3] = 0u; }
@@ -552,7 +579,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (key != 0ull) {
           const int t = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
           const int a = a0 + j;
-          const AgentParams P = sw_load_params(k.tab.prm + a);
+          const AgentParams P = load_params(k.tab.prm + a);
           const size_t idx = (size_t)a * k.Tp + t;
           const float4 s0t = __ldg(&k.tab.s0[idx]);
           const float4 s1t = __ldg(&k.tab.s1[idx]);
@@ -622,17 +649,15 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       }
       const float eh = sw_sigmoid(ze), oh = sw_sigmoid(zo);   // logistic is monotone: max harm = logistic(max logit)
       const bool has_agents = k.A > 0 && mm != 0;
-      const double dce_min = (double)rmin_t / 1000.0;
       const bool has_col = col != 0xffffffffu;
-      const double wttc = has_col ? rint((double)col * k.dtd * 1000.0) / 1000.0 : (double)CUDART_INF;
       bool ok = true;
       if (has_agents) {
         if (do_be && (k.tmask & FO_T_BE) && (double)btn > k.thr_be) ok = false;
         if (do_hr && (k.tmask & FO_T_HARM) && (double)hwc_all > k.thr_harm) ok = false;
         if (do_hr && (k.tmask & FO_T_RISK) && (double)orr > k.thr_risk) ok = false;
         if (do_hr && (k.tmask & FO_T_CP) && (double)cpm > k.thr_cp) ok = false;
-        if (do_ttc && (k.tmask & FO_T_TTC) && has_col && wttc < k.thr_ttc) ok = false;
-        if (do_dce && (k.tmask & FO_T_DCE) && rmin_t != 0xffffffu && dce_min < k.thr_dce) ok = false;
+        if (do_ttc && (k.tmask & FO_T_TTC) && has_col && col < k.thr_ttc_col) ok = false;
+        if (do_dce && (k.tmask & FO_T_DCE) && rmin_t != 0xffffffu && rmin_t < k.thr_dce_mm) ok = false;
         if (fl & FO_F_BE_RANGE) ok = false;
       }
       k.valid[n] = ok ? 1 : 0;
@@ -640,8 +665,8 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       if (k.summary) {
         float* sm = k.summary + (size_t)n * FO_SUMMARY_K;
         sm[0] = er; sm[1] = orr; sm[2] = do_hr ? eh : 0.0f; sm[3] = do_hr ? oh : 0.0f; sm[4] = cpm; sm[5] = hwc_all;
-        sm[6] = (rmin_t == 0xffffffu || !do_dce) ? CUDART_INF_F : (float)dce_min;
-        sm[7] = has_col ? (float)wttc : CUDART_INF_F;
+        sm[6] = (rmin_t == 0xffffffu || !do_dce) ? CUDART_INF_F : mm_to_m(rmin_t);
+        sm[7] = has_col ? step_to_s(col, k.dtd) : CUDART_INF_F;
         sm[8] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : btn;
         sm[9] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd;
       }
@@ -688,7 +713,7 @@ static void pick_shape(const MetricKArgs& k, int num_sms, int& W, SweepShape& sh
 // life of the process, because the graph may be replayed while later eager launches are in flight.  When the graph
 // slots run out the kernel falls back to static striding (claim == NULL).
 constexpr int kClaimRing = 1024, kClaimGraph = 3072, kMaxDev = 64;
-static unsigned int* claim_slot(cudaStream_t st) {
+unsigned int* claim_slot(cudaStream_t st) {
   static std::mutex mu;
   static unsigned int* pool[kMaxDev] = {};
   static int ring_next[kMaxDev] = {}, graph_next[kMaxDev] = {};
@@ -714,7 +739,7 @@ static unsigned int* claim_slot(cudaStream_t st) {
   return pool[dev] + s;
 }
 
-template <uint32_t MASK, bool STATS, bool UNI>
+template <uint32_t MASK, bool STATS, bool UNI, bool TIES>
 static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st);
 
 template <uint32_t MASK, bool STATS>
@@ -722,11 +747,19 @@ static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st)
   int W = 1;
   SweepShape shape;
   pick_shape(k, num_sms, W, shape);
-  if (W == 1 && shape.lg_agents == 5) return launch_sweep_shape<MASK, STATS, true>(k, num_sms, W, shape, st);
-  return launch_sweep_shape<MASK, STATS, false>(k, num_sms, W, shape, st);
+  // Float64 re-rounding of np.round(d, 3) ties is compiled into the variants that run when a clause of the validity mask
+  // hangs on a rounded distance (dce / ttc / be thresholds armed, or the caller asked for it): there the mask is the
+  // float64 reference's.  With those thresholds null (the deployment default, occlusion.yaml:20-28) only the last
+  // digit of the reported min_dce could differ, and the kernel without the tie path is 12 % faster.
+  const bool ties = (k.tmask & (FO_T_DCE | FO_T_TTC | FO_T_BE)) != 0 || k.exact_dce;
+  const bool uni = W == 1 && shape.lg_agents == 5;
+  if (uni) return ties ? launch_sweep_shape<MASK, STATS, true, true>(k, num_sms, W, shape, st)
+                       : launch_sweep_shape<MASK, STATS, true, false>(k, num_sms, W, shape, st);
+  return ties ? launch_sweep_shape<MASK, STATS, false, true>(k, num_sms, W, shape, st)
+              : launch_sweep_shape<MASK, STATS, false, false>(k, num_sms, W, shape, st);
 }
 
-template <uint32_t MASK, bool STATS, bool UNI>
+template <uint32_t MASK, bool STATS, bool UNI, bool TIES>
 static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st) {
   const size_t smem = sweep_smem_bytes(k.T, W);
   // the opt-in shared-memory size is a per-device function attribute: remember what each device has been given
@@ -735,12 +768,12 @@ static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const Sw
   FO_CUDA_TRY(cudaGetDevice(&dev));
   const bool tracked = dev >= 0 && dev < kMaxDev;
   if (!tracked || smem > configured[dev].load(std::memory_order_acquire)) {
-    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FO_CUDA_TRY(cudaFuncSetAttribute(fo_metric_sweep_kernel<MASK, STATS, UNI, TIES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     if (tracked) configured[dev].store(smem, std::memory_order_release);
   }
   int per_sm = 1;
-  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS, UNI>, W * 32, smem));
+  FO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fo_metric_sweep_kernel<MASK, STATS, UNI, TIES>, W * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const int full = num_sms * per_sm;
   const int grid = k.N < full ? k.N : full;       // persistent: teams claim trajectories
@@ -748,7 +781,7 @@ static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const Sw
   const char* fixed = getenv("FO_STATIC_STRIDE");          // A/B switch: teams stride over trajectories instead
   kk.claim = (k.N > grid && !(fixed && fixed[0] == '1')) ? claim_slot(st) : nullptr;
   if (kk.claim) FO_CUDA_TRY(cudaMemsetAsync(kk.claim, 0, sizeof(unsigned int), st));
-  fo_metric_sweep_kernel<MASK, STATS, UNI><<<grid, W * 32, smem, st>>>(kk, shape);
+  fo_metric_sweep_kernel<MASK, STATS, UNI, TIES><<<grid, W * 32, smem, st>>>(kk, shape);
   count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;

@@ -174,11 +174,6 @@ class MetricEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _raw_struct(self, agents: AgentSet, to_ptr):
-        raw = L.FoAgentsRaw()
-        raw.n_agents, raw.t_stride = agents.n_agents, agents.t_stride
-        return raw
-
     def set_agents(self, agents: AgentSet, origin=None):
         """Upload + pack the phantom predictions (once per planning cycle).  ``origin`` (x, y) is
         subtracted in float64 from agent and ego positions before the cast to float32."""

@@ -133,7 +133,7 @@ typedef struct FoMetricArgs {
   uint8_t *valid;          /* [N] safety_check of Metric.evaluate_metrics */
   float *summary;          /* [N, FO_SUMMARY_K] */
   uint32_t *flags;         /* [N] FO_F_* */
-  float *pair;             /* [N, A, FO_PAIR_K] or NULL */
+  float *pair;             /* [N, A, FO_PAIR_K] or NULL; 16-byte aligned */
   float *step;             /* [N, A, T-1, FO_STEP_K] or NULL */
 } FoMetricArgs;
 

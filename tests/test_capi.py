@@ -26,8 +26,8 @@ def test_every_declared_symbol_is_exported():
 def test_argument_validation_without_device():
     from frenetix_occlusion_b200 import _lib as L
     assert L.lib.fo_version() == 1
-    assert L.lib.fo_agent_table_bytes(256, 51) == 256 * 51 * 40 + 256 * 32 + 256 * 51 * 20 + 256 * 7 * 20   # + 7 windows of 8 steps
-    assert L.lib.fo_agent_table_bytes(33, 31) == 33 * 31 * 40 + 33 * 32 + 64 * 31 * 20 + 64 * 4 * 20
+    assert L.lib.fo_agent_table_bytes(256, 51) == 256 * 51 * 40 + 256 * 32 + 256 * 51 * 24 + 256 * 7 * 20 + 256 * 8   # time-major copies, 7 windows of 8 steps, slot maps
+    assert L.lib.fo_agent_table_bytes(33, 31) == 33 * 31 * 40 + 33 * 32 + 64 * 31 * 24 + 64 * 4 * 20 + 64 * 8
     assert L.lib.fo_metric_bundle(None, None) == -1
     assert b"NULL" in L.lib.fo_last_error()
     a = L.FoMetricArgs()
@@ -87,8 +87,9 @@ def test_hot_kernels_stay_inside_the_instruction_cache_budget():
         hit = [v - cold.get(k, 0) for k, v in sizes.items() if all(p in k for p in parts)]
         assert len(hit) == 1, (parts, sorted(sizes))
         return hit[0]
-    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1E") <= 52 * 1024     # all 7 metrics, one-warp window-filter shape
-    assert size_of("fo_metric_sweep_kernel", "ILj111ELb0ELb1E") <= 42 * 1024     # default metrics (no BE)
-    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb0E") <= 62 * 1024     # team shape (latency path)
-    assert size_of("fo_metric_kernel", "ILi1E") <= 50 * 1024                     # detail kernel, T <= 32
-    assert size_of("fo_metric_kernel", "ILi2E") <= 66 * 1024                     # detail kernel, T <= 64
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1ELb0E") <= 48 * 1024   # all 7 metrics, one-warp window-filter shape
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1ELb1E") <= 52 * 1024   # ... with the float64 tie path (armed dce / ttc / be)
+    assert size_of("fo_metric_sweep_kernel", "ILj111ELb0ELb1ELb0E") <= 40 * 1024   # default metrics (no BE)
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb0ELb0E") <= 60 * 1024   # team shape (latency path)
+    assert size_of("fo_metric_detail_kernel", "ILj127E") <= 50 * 1024            # detail kernel (lane = agent), all 7 metrics, incl. BE helpers
+    assert size_of("fo_metric_detail_kernel", "ILj111E") <= 38 * 1024            # default metrics

@@ -14,7 +14,9 @@ import parity
 pytestmark = pytest.mark.gpu
 
 
-def _check(rep, max_tie_rate=0.03):
+def _check(rep, max_tie_rate=0.005):
+    """Documented exact-threshold ties are bounded at 0.5 % of the pairs -- the observed level is 0.14 %,
+    all of them risk-argmax indices of two float32 products equal within rounding."""
     assert not rep["fail"], "\n".join(rep["fail"])
     n_ties = sum(rep["ties"].values())
     assert n_ties <= max(3, max_tie_rate * rep["n_pairs"]), rep["ties"]
@@ -227,6 +229,36 @@ def test_ragged_agent_lengths_window_filter(cuda_device, monkeypatch):
     out = MO.evaluate_bundle(case)
     res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
     _check(parity.compare_bundle(out, res, case))
+
+
+@pytest.mark.parametrize("thr", [{"dce": 0.75, "ttc": 1.2}, {"dce": 0.3, "ttc": None}, {"dce": None, "ttc": 2.0}])
+def test_armed_distance_thresholds_on_the_window_filter_shape(thr, cuda_device, monkeypatch):
+    """dce / ttc thresholds armed on the throughput shape (one warp per trajectory, window filter): the clauses compare
+    np.round(d, 3) in float64 (dce.py:79, ttc.py:43, metric.py:85-98), so the summary kernel runs its float64 tie
+    re-rounding variant and the mask must equal the oracle's bit for bit -- no tie allowance for dce rounding."""
+    monkeypatch.setenv("FO_TEAM_WARPS", "1")
+    thresholds = {"harm": None, "risk": None, "be": None, "cp": None, "wttc": None, "ttce": None, **thr}
+    case = S.make_case(4000, 48, 51, seed=93, thresholds=thresholds)
+    out = MO.evaluate_bundle(case)
+    res, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    rep = parity.compare_bundle(out, res, case)
+    assert not rep["fail"], "\n".join(rep["fail"])
+    ok = ~out["be_error"] & ((res["flags"] & 1) == 0)
+    assert np.array_equal(res["valid"].astype(bool)[ok], out["valid"][ok])
+    assert np.array_equal(np.round(res["summary"][ok, 6].astype(np.float64), 3), out["dce"].min(1)[ok])
+    assert 0 < out["valid"].sum() < len(out["valid"])          # the clauses really decide something here
+
+
+def test_exact_dce_switch_matches_detail_kernel(cuda_device, monkeypatch):
+    """FO_EXACT_DCE=1 turns the float64 tie re-rounding on without any armed distance threshold: min_dce of the
+    summary kernel then equals the detail kernel's on every trajectory."""
+    monkeypatch.setenv("FO_TEAM_WARPS", "1")
+    monkeypatch.setenv("FO_EXACT_DCE", "1")
+    case = S.make_case(3000, 64, 51, seed=94)
+    res_d, _ = parity.run_gpu(case, want_pair=True, want_step=False)
+    res_s, _ = parity.run_gpu(case, want_pair=False, want_step=False)
+    assert np.array_equal(res_d["summary"][:, 6], res_s["summary"][:, 6])
+    assert np.array_equal(res_d["summary"][:, 7], res_s["summary"][:, 7])
 
 
 def test_claimed_trajectories_equal_static_striding(cuda_device, monkeypatch):
