@@ -183,7 +183,7 @@ class OAPVehicleAgent(OAPAgent):
                                    velocity=self.initial_velocity, time_step=0)
         vf = config["prediction"]["variance_factor"]
         J = len(self.reference_paths)
-        ro = self._rollout_path(self.reference_paths, pos, velocity, vf)
+        ro = self._rollout_path([self._path_window(p, pos, velocity, horizon) for p in self.reference_paths], pos, velocity, vf)
         n = int(horizon / dt) + 1
         smp = ro["sample"]
         valid = [j for j in range(J) if smp[j] >= 0]
@@ -198,6 +198,22 @@ class OAPVehicleAgent(OAPAgent):
             best = min(range(len(valid)), key=lambda q: heading_var(self.reference_paths[valid[q]]))
             self._full_prediction = self._all_predictions[best]
         self.predictions = self._create_cr_predictions(0)
+
+    @staticmethod
+    def _path_window(path, pos, velocity, horizon, max_points=1024):
+        """The rollout kernel stages at most 1024 polyline points per job: keep the part of a long route the agent can
+        reach within its horizon (10 m behind the projection of its start, 1.3 x the distance at the fastest sampled
+        end speed plus 20 m ahead)."""
+        path = np.asarray(path, dtype=np.float64)
+        if len(path) <= max_points:
+            return path
+        cum = np.concatenate(([0.0], np.cumsum(np.hypot(*np.diff(path, axis=0).T))))
+        k0 = int(np.argmin(np.hypot(*(path - np.asarray(pos, dtype=np.float64)).T)))
+        lo = int(np.searchsorted(cum, cum[k0] - 10.0))
+        hi = int(np.searchsorted(cum, cum[k0] + 1.3 * 1.2 * float(velocity) * float(horizon) + 20.0)) + 1
+        lo = max(min(lo, len(path) - 2), 0)
+        hi = min(max(hi, lo + 2), len(path), lo + max_points)
+        return path[lo:hi]
 
     def _create_cr_predictions(self, timestep) -> list:
         """agent.py:398-426: one prediction per route reference path; covariances restart at 0.1 for the sliced list

@@ -1,9 +1,14 @@
 """Route exploration for vehicle phantoms (mirror of reference route_planner.py:14-93).
 
 Depth-first walk over lanelet successors and same-direction neighbours, ``max_depth = 2``; one
-reference polyline per route = concatenated lanelet centre lines (the reference delegates this to
-commonroad_route_planner 2022.3 ``Route.reference_path`` -- not installable; PARITY UNPINNED for the
-smoothing/resampling that library applies)."""
+reference polyline per route (the reference delegates this to commonroad_route_planner 2022.3
+``Route.reference_path`` -- not installable, PARITY UNPINNED): centre lines of the route's lanelets chained without
+the duplicated joint vertices, lanelets that are only crossed by a lane change skipped, resampled at a fixed 2 m
+step and smoothed with four Chaikin corner-cutting refinements, as that library does.
+
+The two graph-walk methods ``_find_all_routes`` / ``_explore_routes`` follow reference route_planner.py:54-90
+statement by statement (same traversal order decides the order of the predictions); SURVEY.md 2 lists the route
+planner as out of scope as code -- it is host glue that only produces the kernel's input polylines."""
 from __future__ import annotations
 
 from typing import List
@@ -12,14 +17,11 @@ import numpy as np
 
 
 def lanelet_orientation_at_position(lanelet, pos):
-    """Heading of the centre-line segment closest to ``pos`` (commonroad_route_planner utility)."""
+    """commonroad_route_planner.utility.route.lanelet_orientation_at_position (2022.3): heading of the centre-line
+    segment that STARTS at the centre vertex closest to ``pos`` (the last vertex is not a candidate)."""
     c = np.asarray(lanelet.center_vertices, dtype=np.float64)
-    seg = c[1:] - c[:-1]
-    l2 = np.maximum((seg ** 2).sum(1), 1e-12)
-    u = np.clip(((np.asarray(pos) - c[:-1]) * seg).sum(1) / l2, 0.0, 1.0)
-    q = c[:-1] + u[:, None] * seg
-    j = int(np.argmin(np.hypot(*(np.asarray(pos) - q).T)))
-    return float(np.arctan2(seg[j, 1], seg[j, 0]))
+    k = int(np.argmin(np.hypot(*(np.asarray(pos, dtype=np.float64) - c[:-1]).T)))
+    return float(np.arctan2(c[k + 1, 1] - c[k, 1], c[k + 1, 0] - c[k, 0]))
 
 
 def resample_polyline(pts, step=1.0):
@@ -30,6 +32,42 @@ def resample_polyline(pts, step=1.0):
     n = max(2, int(np.ceil(cum[-1] / step)) + 1)
     s = np.linspace(0.0, cum[-1], n)
     return np.stack((np.interp(s, cum, pts[:, 0]), np.interp(s, cum, pts[:, 1])), -1)
+
+
+def resample_fixed_step(pts, step=2.0):
+    """Points at arc lengths 0, step, 2 step, ... plus the last point (commonroad_route_planner ``resample_polyline``)."""
+    pts = np.asarray(pts, dtype=np.float64)
+    cum = np.concatenate(([0.0], np.cumsum(np.hypot(*np.diff(pts, axis=0).T))))
+    n = max(int(np.floor(cum[-1] / step)), 1)
+    s = np.arange(n + 1) * step
+    if cum[-1] - s[-1] > 1e-9:
+        s = np.concatenate((s, [cum[-1]]))
+    return np.stack((np.interp(s, cum, pts[:, 0]), np.interp(s, cum, pts[:, 1])), -1)
+
+
+def chaikins_corner_cutting(pts, refinements=4):
+    """Each refinement replaces every edge by its 1/4 and 3/4 points; the end points stay."""
+    p = np.asarray(pts, dtype=np.float64)
+    for _ in range(refinements):
+        q = np.empty((2 * (len(p) - 1), 2))
+        q[0::2] = 0.75 * p[:-1] + 0.25 * p[1:]
+        q[1::2] = 0.25 * p[:-1] + 0.75 * p[1:]
+        p = np.concatenate((p[:1], q, p[-1:]))
+    return p
+
+
+def route_reference_path(lanelet_network, route):
+    """``Route.reference_path`` of commonroad_route_planner for a list of lanelet ids."""
+    parts = []
+    for a, b in zip(route, list(route[1:]) + [None]):
+        la = lanelet_network.find_lanelet_by_id(a)
+        if b is not None and b not in la.successor:
+            continue                                   # lane change: the neighbour's centre line takes over
+        c = np.asarray(la.center_vertices, dtype=np.float64)
+        if parts and np.allclose(parts[-1][-1], c[0]):
+            c = c[1:]
+        parts.append(c)
+    return chaikins_corner_cutting(resample_fixed_step(np.concatenate(parts), 2.0), 4)
 
 
 class FORoutePlanner:
@@ -53,8 +91,7 @@ class FORoutePlanner:
         self.route_candidates = [r for r in self._find_all_routes(ids[0], max_depth=2) if r]
         self.reference_paths = []
         for route in self.route_candidates:
-            pts = np.concatenate([self.lanelet_network.find_lanelet_by_id(i).center_vertices for i in route])
-            self.reference_paths.append(resample_polyline(pts, 1.0))
+            self.reference_paths.append(route_reference_path(self.lanelet_network, route))
         return self.reference_paths
 
     def _find_all_routes(self, id_lanelet_start, max_depth=2):

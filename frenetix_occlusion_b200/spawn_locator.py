@@ -389,7 +389,23 @@ class SpawnLocator:
         starts = np.nonzero(occ & ~np.concatenate(([False], occ[:-1])))[0]
         if len(starts) > 1 and self.debug:
             print("MultiLineString in spawn point processing detected")
-        intersection = P[starts[-1]] if len(starts) > 1 else P[starts[0]]
+        k = int(starts[-1] if len(starts) > 1 else starts[0])
+        intersection = P[k]
+        if k > 0:
+            # the reference intersects the path with the occluded polygon exactly (spawn_locator.py:521-529): refine the
+            # 5 cm bracket [not occluded, occluded] with two more classified batches of 33 points -> 0.05 mm
+            lo_s, hi_s = ss[k - 1], ss[k]
+            for _ in range(2):
+                cs = np.linspace(lo_s, hi_s, 33)
+                Pc = np.stack((np.interp(cs, cum, path[:, 0]), np.interp(cs, cum, path[:, 1])), -1)
+                oc = np.atleast_1d(self.sensor_model.occluded_area.contains(Pc))
+                oc[-1] = True
+                j = int(np.argmax(oc))
+                if j == 0:
+                    hi_s = lo_s
+                    break
+                lo_s, hi_s = cs[j - 1], cs[j]
+            intersection = np.array([np.interp(hi_s, cum, path[:, 0]), np.interp(hi_s, cum, path[:, 1])])
         s_intersection = self.cosy_cl.convert_to_curvilinear_coords(intersection[0], intersection[1])[0]
         s_phantom = s_intersection + self.phantom_offset_s[ego_intention]
         if s_phantom > self.s_threshold or s_phantom < self.ego_cl[0] + 3:

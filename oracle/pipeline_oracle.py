@@ -1,94 +1,150 @@
-"""CPU oracle of the whole per-planning-cycle pipeline (visibility -> spawn points -> phantom predictions ->
-dense metric core).  TEST INFRASTRUCTURE: only ``tests/``, ``oracle/make_scenario_golden.py`` and
-``__graft_entry__.smoke()`` use it.
+"""Oracle of the whole per-planning-cycle pipeline: the REFERENCE'S OWN ``FOInterface`` (``interface.py``) with its own
+``sensor_model.py``, ``spawn_locator.py``, ``agent.py``, ``route_planner.py``, ``utils/{fo_obstacle,helper_functions,
+frenetix_handler,sampling}.py`` and ``metrics/*`` imported **unmodified** from ``/root/reference`` and run over stand-ins for
+the third-party packages this image cannot install.  TEST INFRASTRUCTURE: only ``oracle/make_scenario_golden.py``
+(build container) uses it; it imports nothing of ``frenetix_occlusion_b200``.
 
-PARITY UNPINNED for stages 1-2 and the spawn locator: the reference needs shapely / commonroad / frenetix, none
-of which can be installed, and ships no test vectors.  What this oracle pins is the DEVICE side of the product:
-every call the host classes make into ``libfo_b200.so`` -- ray casting, point classification, CV / path rollouts,
-the metric bundle -- is replaced by the float64 numpy restatement of the reference's construction
-(``oracle/visibility_oracle.py``, ``oracle/metric_oracle.py``), while the host bookkeeping of
-``frenetix_occlusion_b200`` (thresholds, sorting, raster components: no arithmetic of the path) is shared.
-The scenario goldens under ``tests/golden/scene_*.json`` are produced with it on the CPU."""
+What is the reference's: every threshold, ordering, filter chain and piece of control flow of the visibility
+computation (``sensor_model.py:41-193``), the three spawn-point finders (``spawn_locator.py:80-578``), the agent manager and
+agents (``agent.py``), the vehicle sampling matrix and selection (``frenetix_handler.py``, ``agent.py:364-426``), the metric
+plugins and the validity clauses (``metrics/metric.py:35-100``).  What is restated (PARITY UNPINNED at these leaves, listed
+with their pinned versions in the headers of the stand-in modules):
+
+* shapely 2.0.2 / GEOS                          -> ``oracle/polygon.py`` (float64 overlay, buffers, predicates)
+* commonroad-io 2023.2 object model             -> ``oracle/ref_world.py`` (scene dict of the fixtures) + ``oracle/ref_shims.py``
+* commonroad-drivability-checker 2023.1         -> ``ref_world.CurvilinearCoordinateSystem``, polyline utilities, ``RectOBB``
+* commonroad-route-planner 2022.3               -> ``ref_world.Route``, ``lanelet_orientation_at_position``
+* frenetix (C++)                                -> ``ref_world.TrajectoryHandler`` etc.
+* scipy 1.12 ``mvn.mvnun``                      -> ``ref_shims.mvnun``
+* matplotlib visualisation                      -> no-op ``ref_world.FOVisualization``
+"""
 from __future__ import annotations
 
+import random
+import sys
 import types
 
 import numpy as np
 
-from frenetix_occlusion_b200 import agent as A
-from frenetix_occlusion_b200 import sensor_model as SM
-from frenetix_occlusion_b200.interface import FOInterface
+from . import polygon as G
+from . import ref_shims
+from . import ref_world as W
 
-from . import metric_oracle as MO
-from . import visibility_oracle as VO
-
-
-class _HostFrame:
-    def __init__(self, origin, heading, rect, flags, boundary, polygons, radius, fov):
-        self.origin = np.asarray(origin, dtype=np.float64)
-        self.ego = np.array([self.origin[0], self.origin[1], float(heading)])
-        # the device path sees float32 values relative to the ego: round the same way so both sides
-        # consume identical numbers
-        f32 = lambda a: np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)  # noqa: E731
-        r = np.array(rect, dtype=np.float64).reshape(-1, 5)
-        r[:, :2] -= self.origin
-        self.rect = f32(r)
-        self.flags = np.asarray(flags, dtype=np.uint8).reshape(-1)
-        b = np.zeros((0, 4)) if boundary is None else np.asarray(boundary, dtype=np.float64).reshape(-1, 4)
-        self.boundary = f32(b - np.tile(self.origin, 2))
-        self.polygons = [f32(np.asarray(p, dtype=np.float64) - self.origin) for p in polygons]
-        self.radius, self.fov = float(radius), float(fov)
-        self.n_obstacles = len(self.rect)
-        self.heading = float(np.float32(heading))
+REFERENCE_CONFIG = "/root/reference/configurations/simulation/occlusion.yaml"
+_done = False
 
 
-class OracleSensorModel(SM.SensorModel):
-    def _build_frame(self, rect, flags, border):
-        return _HostFrame(self.ego_pos, self.ego_orientation, rect, flags, border, self.lanelet_polygons,
-                          self.sensor_radius, self.sensor_angle)
-
-    def _raycast(self):
-        f = self._frame
-        rng, hit, vis = VO.raycast(np.array([0.0, 0.0, f.heading]), f.rect, f.flags, f.boundary, f.radius, f.fov,
-                                   self.n_rays)
-        return rng, hit, vis
-
-    def _classify(self, points, focus=-1, focus_margin=0.0):
-        f = self._frame
-        P = np.asarray(points, dtype=np.float64).reshape(-1, 2) - f.origin
-        P = P.astype(np.float32).astype(np.float64)
-        flags, lan = VO.classify_points(P, np.array([0.0, 0.0, f.heading]), f.rect, f.flags, f.boundary, f.polygons,
-                                        f.radius, f.fov, 1.5 * f.radius, focus=focus, focus_margin=focus_margin)
-        return flags, np.full(len(P), VO.HIT_NONE, dtype=np.int32), lan
+def _rotate(geom, angle, origin=(0, 0), use_radians=False):
+    a = float(angle) if use_radians else np.radians(float(angle))
+    c, s = np.cos(a), np.sin(a)
+    o = np.asarray(origin, dtype=np.float64)
+    rot = lambda r: (np.asarray(r) - o) @ np.array([[c, s], [-s, c]]) + o  # noqa: E731
+    return G.Polygon(rot(geom._shell), [rot(h) for h in geom._holes])
 
 
-class _OracleRollouts:
-    def _rollout_cv(self, pos, velocity, phi, var_factor):
-        r = VO.rollout_cv([pos[0]], [pos[1]], [velocity], [phi], self.dt, self.horizon, 0.1, var_factor)
-        return {k: r[k].astype(np.float32).astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
-
-    def _rollout_path(self, paths, pos, velocity, var_factor):
-        rows = [VO.rollout_path(p, pos[0], pos[1], velocity, self.dt, self.horizon, 3.0, 0.1, var_factor) for p in paths]
-        out = {k: np.stack([r[k] for r in rows]).astype(np.float32).astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
-        out["sample"] = np.array([r["sample"] for r in rows])
-        return out
+def _translate(geom, xoff=0.0, yoff=0.0):
+    t = np.array([float(xoff), float(yoff)])
+    return G.Polygon(geom._shell + t, [h + t for h in geom._holes])
 
 
-class OraclePedestrianAgent(_OracleRollouts, A.OAPPedestrianAgent):
-    pass
+def install():
+    """Register every stand-in and put the reference tree on ``sys.path``."""
+    global _done
+    if _done:
+        return
+    ref_shims.install()
+    m = ref_shims._module
+    sh = m("shapely")
+    sh.geometry = m("shapely.geometry", Point=G.Point, Polygon=G.Polygon, MultiPolygon=G.MultiPolygon, LineString=G.LineString,
+                    MultiPoint=G.MultiPoint, MultiLineString=G.MultiLineString, GeometryCollection=G.GeometryCollection)
+    m("shapely.geometry.multipolygon", MultiPolygon=G.MultiPolygon)
+    sh.affinity = m("shapely.affinity", rotate=_rotate, translate=_translate)
+    sh.ops = m("shapely.ops", unary_union=G.unary_union)
+    dc = sys.modules["commonroad_dc"]
+    dc.pycrccosy = m("commonroad_dc.pycrccosy", CurvilinearCoordinateSystem=W.CurvilinearCoordinateSystem)
+    dc.geometry = m("commonroad_dc.geometry")
+    dc.geometry.util = m("commonroad_dc.geometry.util", compute_pathlength_from_polyline=W.compute_pathlength_from_polyline,
+                         compute_curvature_from_polyline=W.compute_curvature_from_polyline)
+    crp = m("commonroad_route_planner")
+    crp.route_planner = m("commonroad_route_planner.route_planner", Route=W.Route)
+    crp.route = m("commonroad_route_planner.route", RouteType=W.RouteType, Route=W.Route)
+    crp.utility = m("commonroad_route_planner.utility")
+    crp.utility.route = m("commonroad_route_planner.utility.route",
+                          lanelet_orientation_at_position=W.lanelet_orientation_at_position)
+    fx = m("frenetix", TrajectoryHandler=W.TrajectoryHandler, CoordinateSystemWrapper=W.CoordinateSystemWrapper)
+    fx.trajectory_functions = m("frenetix.trajectory_functions", FillCoordinates=W.FillCoordinates)
+    fx.trajectory_functions.feasability_functions = m(
+        "frenetix.trajectory_functions.feasability_functions",
+        CheckYawRateConstraint=W._feasability("yaw_rate"), CheckAccelerationConstraint=W._feasability("acceleration"),
+        CheckCurvatureConstraint=W._feasability("curvature"), CheckCurvatureRateConstraint=W._feasability("curvature_rate"))
+    # utils/visualization.py pulls in matplotlib (TkAgg) and the commonroad renderer: replaced as a whole module
+    import frenetix_occlusion.utils as ref_utils          # the reference's package (plain directory import)
+    vis = m("frenetix_occlusion.utils.visualization", FOVisualization=W.FOVisualization)
+    ref_utils.visualization = vis
+    _done = True
 
 
-class OracleVehicleAgent(_OracleRollouts, A.OAPVehicleAgent):
-    pass
+def reference_interface():
+    install()
+    import frenetix_occlusion.interface as ref_interface
+    return ref_interface
 
 
-class OracleAgentManager(A.FOAgentManager):
-    pedestrian_cls = OraclePedestrianAgent
-    vehicle_cls = OracleVehicleAgent
+class TrajectoryStub:
+    """The planner's trajectory duck type: ``.cartesian.{x,y,theta,v,a}``."""
+
+    def __init__(self, arr):
+        a = np.asarray(arr, dtype=np.float64)
+        self.cartesian = types.SimpleNamespace(x=a[:, 0].copy(), y=a[:, 1].copy(), theta=a[:, 2].copy(), v=a[:, 3].copy(),
+                                               a=a[:, 4].copy())
+        self.costMap, self.feasabilityMap = {}, {}
+        self.cost, self.feasible, self.valid, self.uniqueId, self.sampling_parameters = 0.0, True, True, 0, None
+
+
+def run_cycles(scene: dict, reference_path, vehicle_params, cycles, config_path=REFERENCE_CONFIG, seed=7):
+    """Drive the reference's ``FOInterface`` over planning cycles.
+
+    ``cycles``: list of dicts with the planner-side INPUTS of one cycle -- ``timestep``, ``ego_pos``, ``ego_orientation``,
+    ``ego_pos_cl``, ``ego_v`` and optionally ``fan`` ([N, T, 5] trajectories to assess).  Returns one record per cycle
+    with the reference's own outputs."""
+    ref_interface = reference_interface()
+    random.seed(seed)                                     # agent ids: randint(10000, 11000), agent.py:190
+    sc = W.Scenario(scene)
+    path = np.asarray(reference_path, dtype=np.float64)
+    vp = types.SimpleNamespace(**vehicle_params) if isinstance(vehicle_params, dict) else vehicle_params
+    fo = ref_interface.FOInterface(sc, path, vp, sc.dt, config_path=config_path)
+    cosy = W.CurvilinearCoordinateSystem(path)
+    out = []
+    for c in cycles:
+        predictions = {}
+        fo.evaluate_scenario(predictions, np.asarray(c["ego_pos"], dtype=np.float64), float(c["ego_orientation"]),
+                             np.asarray(c["ego_pos_cl"], dtype=np.float64), float(c["ego_v"]), int(c["timestep"]), cosy)
+        am = fo.agent_manager
+        rec = {"timestep": int(c["timestep"]),
+               "visible_obstacles": list(fo.sensor_model.visible_objects_timestep),
+               "visible_area": float(fo.sensor_model.visible_area.area), "occluded_area": float(fo.sensor_model.occluded_area.area),
+               "spawn_points": [{"position": np.asarray(sp.position, dtype=np.float64), "agent_type": sp.agent_type,
+                                 "source": sp.source, "orientation": sp.orientation} for sp in fo.spawn_points],
+               "predictions": {pid: {"agent_type": am.agent_by_prediction_id(pid).agent_type,
+                                     "pos_list": np.asarray(p["pos_list"], dtype=np.float64),
+                                     "orientation_list": np.asarray(p["orientation_list"], dtype=np.float64),
+                                     "v_list": np.asarray(p["v_list"], dtype=np.float64),
+                                     "cov_list": np.asarray(p["cov_list"], dtype=np.float64), "shape": dict(p["shape"])}
+                               for pid, p in am.predictions.items()}}
+        if c.get("fan") is not None:
+            valid, harm = [], []
+            for tr in np.asarray(c["fan"], dtype=np.float64):
+                res, ok = fo.trajectory_safety_assessment(TrajectoryStub(tr))
+                valid.append(bool(ok))
+                harm.append(float(res["hr"]["max_obst_harm_with_cp_all"]) if "hr" in res else None)
+            rec["valid"], rec["max_obst_harm_with_cp_all"] = valid, harm
+        out.append(rec)
+    return out
 
 
 def case_from_predictions(agent_manager, vehicle_params, ego, activated_metrics, thresholds):
-    """Plain-array case (the format of ``metric_oracle.evaluate_bundle``) from an agent manager."""
+    """Plain-array case (the format of ``metric_oracle.evaluate_bundle``) from any agent manager with the reference's
+    ``predictions`` layout."""
     agents = []
     for pid, pred in agent_manager.predictions.items():
         ag = agent_manager.agent_by_prediction_id(pid)
@@ -100,34 +156,3 @@ def case_from_predictions(agent_manager, vehicle_params, ego, activated_metrics,
     return {"dt": float(agent_manager.dt), "vehicle": {k: g(k) for k in ("length", "width", "mass", "wb_rear_axle", "a_max")},
             "ego": np.asarray(ego, dtype=np.float64), "agents": agents,
             "activated_metrics": list(activated_metrics), "thresholds": dict(thresholds)}
-
-
-class OracleMetric:
-    """Batched stand-in for ``metrics.metric.Metric`` on the float64 oracle."""
-
-    def __init__(self, config, vehicle_params, agent_manager):
-        self.config = config
-        self.metric_thresholds = config["metric_thresholds"]
-        self.vehicle_params = vehicle_params
-        self.agent_manager = agent_manager
-
-    def evaluate_bundle(self, trajectories, want_pair=False, want_step=False):
-        ego = np.asarray(trajectories, dtype=np.float64)
-        case = case_from_predictions(self.agent_manager, self.vehicle_params, ego, self.config["activated_metrics"],
-                                     self.metric_thresholds)
-        out = MO.evaluate_bundle(case, want_detail=False)
-        return types.SimpleNamespace(valid=out["valid"], out=out, case=case)
-
-
-class OracleFOInterface(FOInterface):
-    def _make_sensor_model(self):
-        return OracleSensorModel(lanelet_network=self.lanelet_network, ref_path=self.ego_reference_path,
-                                 sensor_radius=self.sensor_radius, sensor_angle=self.sensor_angle, debug=self.debug)
-
-    def _make_agent_manager(self):
-        return OracleAgentManager(scenario=self.cr_scenario, reference_path=self.ego_reference_path,
-                                  config=self.config["agent_manager"], timestep=self.timestep, dt=self.dt,
-                                  debug=self.debug, fo_obstacles=self.fo_obstacles)
-
-    def _make_metrics(self):
-        return OracleMetric(self.config["metrics"], self.vehicle_params, self.agent_manager)

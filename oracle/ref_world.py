@@ -241,10 +241,10 @@ class CurvilinearCoordinateSystem:
 # commonroad-route-planner
 # ---------------------------------------------------------------------------------------------------------------------
 def lanelet_orientation_at_position(lanelet, position):
+    """Direction from the closest centre vertex (the last one excluded) to its successor."""
     c = lanelet.center_vertices
-    k = int(np.argmin(np.hypot(*(np.asarray(position, dtype=np.float64) - c).T)))
-    v1, v2 = (c[k], c[k + 1]) if k < len(c) - 1 else (c[k - 1], c[k])
-    return float(np.arctan2(v2[1] - v1[1], v2[0] - v1[0]))
+    k = int(np.argmin(np.hypot(*(np.asarray(position, dtype=np.float64) - c[:-1]).T)))
+    return float(np.arctan2(c[k + 1, 1] - c[k, 1], c[k + 1, 0] - c[k, 0]))
 
 
 def _chaikin(polyline, refinements):

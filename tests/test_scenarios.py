@@ -1,10 +1,12 @@
 """Scenario replays (BASELINE.json configs[0..1]): the whole per-cycle pipeline -- visibility -> spawn points ->
 phantom predictions -> dense metric core -- over the reference's three example scenarios.
 
-The committed ``tests/golden/scene_scenario*.json`` hold the compact scenes and the CPU oracle pipeline's
-results (``oracle/make_scenario_golden.py``).  CPU: the oracle still reproduces them.  GPU: the product pipeline
-(``FOInterface`` on the CUDA kernels) gives the same visible obstacles, spawn points, predictions and validity
-masks."""
+The committed ``tests/golden/scene_scenario*.json`` hold the compact scenes, the planner-side inputs of every cycle
+and the OUTPUTS OF THE REFERENCE'S OWN ``FOInterface`` (its ``sensor_model.py``, ``spawn_locator.py``, ``agent.py``,
+``metrics/*`` ... run unmodified over third-party stand-ins, ``oracle/pipeline_oracle.py`` /
+``oracle/make_scenario_golden.py``; no class of the product takes part).  CPU: the reference run still reproduces them
+(build container only).  GPU: the product pipeline (``FOInterface`` on the CUDA kernels) gives the same visible
+obstacles, spawn points (type, source, integer indices, position), predictions and validity masks."""
 import json
 import os
 import random
@@ -32,12 +34,46 @@ def test_scene_fixture_round_trips():
         assert len(sc.lanelet_network.road_border_segments()) > 100
 
 
-def test_oracle_pipeline_reproduces_golden_scenario2():
-    """Fast CPU check (scenario2 has one static obstacle and no configured agents)."""
-    from oracle.make_scenario_golden import run_oracle
+def test_reference_run_reproduces_golden_scenario2():
+    """The reference's own pipeline over the stand-ins still yields the committed outputs (needs /root/reference: build
+    container only -- the GPU box has no reference tree)."""
+    if not os.path.isdir("/root/reference/frenetix_occlusion"):
+        pytest.skip("reference tree not available")
+    from oracle.make_scenario_golden import run_reference
     doc = _load("scene_scenario2.json")
-    got = run_oracle(doc["scene"], doc["timesteps"][:2], doc["agents"])
+    inputs = {"reference_path": doc["inputs"]["reference_path"], "cycles": doc["inputs"]["cycles"][:2]}
+    got = run_reference(doc["scene"], inputs, doc["agents"])
     assert json.loads(json.dumps(got)) == doc["cycles"][:2]
+
+
+def test_pipeline_oracle_is_independent_of_the_product():
+    """The oracle of stages 1-2 must not share code with what it checks: none of its modules imports the product
+    (``make_scenario_golden.py`` uses the replay harness for planner-side INPUTS only)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mod in ("pipeline_oracle.py", "polygon.py", "ref_world.py", "ref_shims.py", "geometry.py"):
+        with open(os.path.join(root, "oracle", mod)) as f:
+            src = f.read()
+        assert not re.search(r"^\s*(from|import)\s+frenetix_occlusion_b200", src, re.M), mod
+    with open(os.path.join(root, "oracle", "make_scenario_golden.py")) as f:
+        src = f.read()
+    used = set(re.findall(r"from frenetix_occlusion_b200(?:\.[\w.]+)? import ([\w, ]+)", src))
+    assert used <= {"replay as R", "scenario_from_dict", "CurvilinearCoordinateSystem", "load_commonroad_xml, scenario_to_dict"}, used
+
+
+def test_fixture_inputs_match_the_replay_harness():
+    """The planner-side inputs stored in the fixtures are what the harness regenerates (so the GPU test below feeds the
+    product exactly what the reference run was fed)."""
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.scenario import scenario_from_dict
+    for name in SCENES:
+        doc = _load(name)
+        ego = R.OpenLoopEgo(scenario_from_dict(doc["scene"]))
+        assert np.allclose(ego.reference_path, doc["inputs"]["reference_path"], rtol=0, atol=1e-8)
+        for c in doc["inputs"]["cycles"]:
+            st = ego.state(c["timestep"])
+            assert np.allclose(st["pos"], c["ego_pos"], atol=1e-9) and abs(st["orientation"] - c["ego_orientation"]) < 1e-12
+            assert np.allclose(st["pos_cl"], c["ego_pos_cl"], atol=1e-9) and st["v"] == c["ego_v"]
 
 
 def test_replay_helpers():
@@ -70,15 +106,20 @@ def test_interface_mirrors_reference_surface():
 
 
 # ------------------------------------------------------------------------------------------- GPU
+# position tolerance per finder [m]: what is left of the sampled geometry after refinement plus the
+# float32 device arithmetic.  Observed on the float64 restatement of the device calls: turn 1e-4, static obstacle 9e-3,
+# dynamic obstacle 3.3e-2 (0.1 m region raster -> centroid)
+POS_TOL = {"left turn": 0.003, "right turn": 0.003, "behind_dynamic_obstacle": 0.045, "behind static obstacle": 0.015}
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SCENES)
-def test_cuda_pipeline_matches_oracle_golden(name, cuda_device):
+def test_cuda_pipeline_matches_reference_golden(name, cuda_device):
     import torch
     from frenetix_occlusion_b200 import replay as R
     from frenetix_occlusion_b200.interface import FOInterface
     from frenetix_occlusion_b200.scenario import scenario_from_dict
-    from oracle import metric_oracle as MO
-    from oracle.pipeline_oracle import case_from_predictions
+    from oracle.make_scenario_golden import obstacle_positions_at, spawn_indices
     doc = _load(name)
     random.seed(7)
     sc = scenario_from_dict(doc["scene"])
@@ -87,35 +128,42 @@ def test_cuda_pipeline_matches_oracle_golden(name, cuda_device):
     fo = FOInterface(sc, ego.reference_path, R.DEFAULT_VEHICLE, sc.dt, config_path=cfg)
     recs = R.replay(fo, ego, doc["timesteps"], fan_kwargs=doc["fan"])
     torch.cuda.synchronize()
-    n_mask_diff = 0
+    hard, ties = 0, 0
     for rec, gold in zip(recs, doc["cycles"]):
         ts = gold["timestep"]
         vis = [int(v) if v < 10000 else "real_agent" for v in rec["visible_obstacles"]]
         assert vis == gold["visible_obstacles"], (ts, vis, gold["visible_obstacles"])
-        # spawn points: same count / type / source (bit-exact "indices"), positions to raster resolution
+        # spawn points: same count / type / source and the same integer indices (closest reference-path sample,
+        # closest scenario obstacle) -- bit-exact; positions to the finder's resolution
         got = [(s["agent_type"], s["source"]) for s in rec["spawn_points"]]
         want = [(s["agent_type"], s["source"]) for s in gold["spawn_points"]]
         assert got == want, (ts, got, want)
+        obst = obstacle_positions_at(doc["scene"], ts)
         for s, g in zip(rec["spawn_points"], gold["spawn_points"]):
-            assert np.allclose(s["position"], g["position"], atol=0.03), (ts, s["position"], g["position"])
+            assert spawn_indices(s["position"], doc["inputs"]["reference_path"], obst) == (g["ref_index"], g["obstacle"]), ts
+            tol = POS_TOL[" ".join(g["source"].split(" ")[:3]) if g["source"].startswith("behind static") else g["source"]]
+            assert np.hypot(*(np.asarray(s["position"]) - g["position"])) <= tol, (ts, g["source"], s["position"], g["position"])
             if g["orientation"] is not None:
                 assert abs(s["orientation"] - g["orientation"]) < 1e-5
-        # predictions of the phantom agents
+        # predictions of the phantom agents (vehicle rollouts: frenetix C++ and the route planner are restated on both
+        # sides, PARITY UNPINNED -- they agree with each other)
         assert len(rec["predictions"]) == len(gold["predictions"])
         for (pid, p), g in zip(rec["predictions"].items(), gold["predictions"]):
             assert rec["agent_types"][pid] == g["agent_type"] and len(p["pos_list"]) == g["n"]
-            assert np.allclose(p["pos_list"][0], g["pos0"], atol=0.03) and np.allclose(p["pos_list"][-1], g["pos_end"], atol=0.06)
-            assert abs(p["v_list"][0] - g["v0"]) < 1e-4
-        # validity mask against the golden mask (spawn positions agree to raster resolution, so the masks may differ
-        # only for trajectories within tolerance of the harm threshold); bit-exactness on identical predictions is
-        # checked in test_cuda_masks_equal_oracle_on_pipeline_predictions
+            assert np.hypot(*(p["pos_list"][0] - np.asarray(g["pos0"]))) <= 0.045
+            assert np.hypot(*(p["pos_list"][-1] - np.asarray(g["pos_end"]))) <= 0.06
+            assert abs(p["orientation_list"][0] - g["yaw0"]) < 2e-3 and abs(p["v_list"][0] - g["v0"]) < 5e-3
+        # validity mask against the REFERENCE's trajectory_safety_assessment over the same fan: identical, except
+        # documented exact-threshold ties (harm within 5e-3 of the 0.1 threshold: the spawn positions differ by the
+        # finder resolution above)
         gold_valid = np.array([c == "1" for c in gold["valid"]])
-        n_mask_diff += int((rec["valid"] != gold_valid).sum())
         diff = rec["valid"] != gold_valid
-        if diff.any() and gold["max_obst_harm_with_cp_all"] is not None:
-            h = np.asarray(gold["max_obst_harm_with_cp_all"])
-            assert np.all(np.abs(h[diff] - 0.1) < 5e-3), (ts, np.nonzero(diff)[0], h[diff])
-    assert n_mask_diff <= 2, n_mask_diff
+        if diff.any():
+            h = np.array([np.nan if v is None else v for v in gold["max_obst_harm_with_cp_all"]], dtype=np.float64)
+            tie = np.abs(h - 0.1) < 5e-3
+            ties += int((diff & tie).sum())
+            hard += int((diff & ~tie).sum())
+    assert hard == 0 and ties <= 1, (hard, ties)
 
 
 @pytest.mark.gpu
