@@ -12,45 +12,59 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _fake_results(lo, hi, k):
-    idx = torch.arange(lo, hi, dtype=torch.float32)
-    valid = (torch.arange(lo, hi) % 3 == 0).to(torch.uint8)
-    summary = idx[:, None] * 0.5 + torch.arange(k, dtype=torch.float32)[None]
-    flags = (torch.arange(lo, hi) % 7 == 0).to(torch.int32)
+def _fake_results(idx, k):
+    idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+    valid = (idx % 3 == 0).to(torch.uint8)
+    summary = idx.to(torch.float32)[:, None] * 0.5 + torch.arange(k, dtype=torch.float32)[None]
+    flags = ((idx % 7 == 0).to(torch.int32)) * 0x01000001          # beyond 2**24: must survive the gather bit for bit
     return valid, summary, flags
 
 
-def _worker(rank, world, n_total, port, q):
+def _worker(rank, world, n_total, block, port, q):
     sys.path.insert(0, ROOT)
-    from frenetix_occlusion_b200.parallel import ResultGatherer, shard_bounds
+    from frenetix_occlusion_b200.parallel import ResultGatherer
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        lo, hi = shard_bounds(n_total, world, rank)
-        g = ResultGatherer(n_total, 10, torch.device("cpu"))
-        v, s, f = _fake_results(lo, hi, 10)
-        gv, gs, gf = g.gather(v, s, f)
-        ev, es, ef = _fake_results(0, n_total, 10)
+        g = ResultGatherer(n_total, 10, torch.device("cpu"), block=block)
+        # the "kernel" writes straight into this rank's slice of the gather buffer
+        out = g.local_result()
+        v, s, f = _fake_results(g.index[rank], 10)
+        out.valid.copy_(v), out.summary.copy_(s), out.flags.copy_(f)
+        gv, gs, gf = g.gather().assembled()
+        ev, es, ef = _fake_results(np.arange(n_total), 10)
         ok = bool(torch.equal(gv, ev) and torch.equal(gs, es) and torch.equal(gf, ef))
-        q.put((rank, ok, lo, hi))
+        q.put((rank, ok, sorted(g.index[rank].tolist())))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [10, 11, 1])
-def test_two_rank_gather(n_total):
+@pytest.mark.parametrize("n_total,block", [(10, 3), (11, None), (1, 4), (4099, 512)])
+def test_two_rank_gather(n_total, block):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + n_total
-    procs = [ctx.Process(target=_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+    port = 29650 + n_total % 97
+    procs = [ctx.Process(target=_worker, args=(r, 2, n_total, block, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert all(ok for _, ok, _, _ in res), res
-    spans = sorted((lo, hi) for _, _, lo, hi in res)
-    assert spans[0][0] == 0 and spans[-1][1] == n_total and spans[0][1] == spans[1][0]
+    assert all(ok for _, ok, _ in res), res
+    owned = sorted(i for _, _, idx in res for i in idx)
+    assert owned == list(range(n_total))                       # every trajectory on exactly one rank
+
+
+def test_interleaved_blocks_balance_a_clustered_bundle():
+    """Blocks of the bundle go round-robin to the ranks: a bundle whose expensive trajectories are clustered (here the
+    second half costs 4x) still gives every rank the same cost within one block."""
+    from frenetix_occlusion_b200.parallel import shard_blocks, shard_indices
+    n, world, block = 1_000_000, 8, 1024
+    cost = np.where(np.arange(n) < n // 2, 1.0, 4.0)
+    per_rank = [cost[shard_indices(n, world, r, block)].sum() for r in range(world)]
+    assert max(per_rank) / min(per_rank) < 1.02          # granularity: one block of ~122 per rank
+    assert shard_blocks(10, 2, 1, 3) == [(3, 6), (9, 10)]
+    assert sum(len(shard_indices(n, world, r, block)) for r in range(world)) == n
 
 
 def test_shard_bounds_cover_everything():
