@@ -1,11 +1,14 @@
 // Stage 1: sensor visibility by ray casting, sm_100a.
 //
-// One CTA = 8 warps = a fan of 256 consecutive rays of one frame; one lane = one ray.  The frame's
-// occluder edges (4 per obstacle rectangle + shared road-border segments) are transformed into the
-// ego frame, culled (outside the sensor disc / outside the fan's angular sector) and compacted into
-// shared memory cooperatively; then every lane walks the staged edge list (all lanes read the same
-// shared-memory word: broadcast, conflict free) with a division-free ray/segment test.  Replaces the
-// shapely clipping of sensor_model.py:103-193 (one polygon difference per border vertex / obstacle).
+// One CTA = 8 warps owns up to 16 fans of 256 consecutive rays of one frame (all 4096 rays of a frame when the call
+// has enough frames to fill the GPU; fewer fans per CTA -- more CTAs per frame -- for the planner's single frame);
+// one lane = one ray per fan, its running first hit lives in registers across the fans' turns.  The frame's occluder
+// edges (4 per obstacle rectangle + shared road-border segments) are transformed into the ego frame, culled against the
+// sensor disc, oriented and compacted into shared memory ONCE per CTA (the transform costs a sincosf per rectangle
+// edge; round 1 redid it for every 256-ray fan); per fan the staged edges are culled against the fan's angular
+// sector into a shared index list, and every lane walks that list (all lanes read the same shared-memory word:
+// broadcast, conflict free) with a division-free ray/segment test.  Replaces the shapely clipping of
+// sensor_model.py:103-193 (one polygon difference per border vertex / obstacle).
 #include <math_constants.h>
 
 #include "fo_common.cuh"
@@ -13,30 +16,29 @@
 namespace fo {
 
 constexpr int kVisThreads = 256;
-constexpr int kVisTile = 1024;   // staged edges per tile: 1024 * (16 + 8) B = 24 KB
+constexpr int kVisTile = 1024;   // staged edges per tile: 1024 * (16 + 8 + 2) B = 26 KB
+constexpr int kVisFans = 16;     // fans one CTA owns at most (one ray per lane and fan)
 constexpr int kVisTrCap = 512;   // listed transparent obstacles per frame (more: fall back to scanning all flags)
 
 struct VisEdge {
   float4 g;   // a.x, a.y, e.x, e.y   (segment a -> a + e, ego frame)
 };
 
-// conservative cull: segment entirely outside the disc of radius R, or entirely outside the angular
-// sector spanned (counter-clockwise) by unit vectors d0 -> d1 with mid direction dm (width <= 180 deg)
-__device__ __forceinline__ bool edge_relevant(float ax, float ay, float bx, float by, float R2, bool use_sector,
-                                              float2 d0, float2 d1, float2 dm) {
-  // distance^2 from the origin to the segment
+// conservative culls.  Disc: segment entirely outside the disc of radius R.  Sector: segment entirely outside the
+// angular sector spanned (counter-clockwise) by unit vectors d0 -> d1 with mid direction dm (width <= 180 deg)
+__device__ __forceinline__ bool edge_in_disc(float ax, float ay, float bx, float by, float R2) {
   float ex = bx - ax, ey = by - ay;
   float l2 = fmaf(ex, ex, ey * ey);
   float t = l2 > 0.0f ? fminf(fmaxf(-(ax * ex + ay * ey) / l2, 0.0f), 1.0f) : 0.0f;
   float px = fmaf(t, ex, ax), py = fmaf(t, ey, ay);
-  if (fmaf(px, px, py * py) > R2) return false;
-  if (use_sector) {
-    float ca = d0.x * ay - d0.y * ax, cb = d0.x * by - d0.y * bx;   // cross(d0, p): < 0 -> clockwise of the fan
-    if (ca < 0.0f && cb < 0.0f) return false;
-    ca = ax * d1.y - ay * d1.x; cb = bx * d1.y - by * d1.x;         // cross(p, d1): < 0 -> beyond the fan
-    if (ca < 0.0f && cb < 0.0f) return false;
-    if (ax * dm.x + ay * dm.y < 0.0f && bx * dm.x + by * dm.y < 0.0f) return false;   // behind the ego
-  }
+  return fmaf(px, px, py * py) <= R2;
+}
+__device__ __forceinline__ bool edge_in_sector(float ax, float ay, float bx, float by, float2 d0, float2 d1, float2 dm) {
+  float ca = d0.x * ay - d0.y * ax, cb = d0.x * by - d0.y * bx;   // cross(d0, p): < 0 -> clockwise of the fan
+  if (ca < 0.0f && cb < 0.0f) return false;
+  ca = ax * d1.y - ay * d1.x; cb = bx * d1.y - by * d1.x;         // cross(p, d1): < 0 -> beyond the fan
+  if (ca < 0.0f && cb < 0.0f) return false;
+  if (ax * dm.x + ay * dm.y < 0.0f && bx * dm.x + by * dm.y < 0.0f) return false;   // behind the ego
   return true;
 }
 
@@ -52,34 +54,26 @@ __device__ __forceinline__ void ray_angle_params(const FoVisibilityArgs& k, floa
   }
 }
 
-__global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisibilityArgs k) {
-  __shared__ float4 sg[kVisTile];
-  __shared__ float2 st[kVisTile];   // (cross(a, e), owner as int bits)
-  __shared__ int s_count;
+__global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisibilityArgs k, const int fans_per_cta) {
+  __shared__ float4 sg[kVisTile];       // a.x, a.y, e.x, e.y of the staged (disc-culled, oriented) edges
+  __shared__ float2 st[kVisTile];       // (cross(a, e), owner as int bits)
+  __shared__ uint16_t s_idx[kVisTile];  // staged edges that touch the current fan's sector
+  __shared__ int s_count, s_nfan;
   __shared__ int s_ntr;                 // transparent (bicycle) obstacles of this frame
   __shared__ uint16_t s_tr[kVisTrCap];
   const int f = blockIdx.y;
-  const int r = blockIdx.x * kVisThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const float ex0 = k.ego[f * 3 + 0], ey0 = k.ego[f * 3 + 1], heading = k.ego[f * 3 + 2];
   float a0, da;
   ray_angle_params(k, heading, a0, da);
   const float R = k.sensor_radius, R2 = R * R;
+  const int fans_total = (k.n_rays + kVisThreads - 1) / kVisThreads;
+  const int fan0 = blockIdx.x * fans_per_cta;
+  const int n_fans = min(fans_per_cta, fans_total - fan0);
 
-  // this lane's ray
-  float c = 1.0f, s = 0.0f;
-  sincosf(a0 + da * (float)r, &s, &c);
-  float best = R;
-  int owner = FO_HIT_NONE;
-
-  // angular sector of this CTA's fan (for culling); fans wider than 180 deg are not culled by angle
-  const int r_lo = blockIdx.x * kVisThreads, r_hi = min(r_lo + kVisThreads, k.n_rays) - 1;
-  const float span = da * (float)(r_hi - r_lo);
-  const bool use_sector = span < 3.0f;
-  float2 d0, d1, dm;
-  sincosf(a0 + da * (float)r_lo - 1e-4f, &d0.y, &d0.x);
-  sincosf(a0 + da * (float)r_hi + 1e-4f, &d1.y, &d1.x);
-  sincosf(a0 + da * 0.5f * (float)(r_lo + r_hi), &dm.y, &dm.x);
+  // a ray's running first hit lives in its output slots between the tiles of a frame with more than kVisTile edges
+  float* const range_f = k.range + (size_t)f * k.n_rays;
+  int32_t* const hit_f = k.hit + (size_t)f * k.n_rays;
 
   const int n_rect_edges = k.n_obstacles * 4;
   const int n_cand = n_rect_edges + k.n_boundary;
@@ -98,12 +92,12 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
       }
     }
   }
-  __syncthreads();
 
   for (int base = 0; base < n_cand; base += kVisTile) {
+    __syncthreads();                       // previous tile fully cast
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    // ---- stage: transform, cull, compact ---------------------------------------------------------
+    // ---- stage ONCE per CTA: transform to the ego frame, cull against the sensor disc, orient, compact ----------
     for (int q0 = base; q0 < min(base + kVisTile, n_cand); q0 += kVisThreads) {
       const int q = q0 + threadIdx.x;
       bool keep = false;
@@ -124,13 +118,13 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
             ax = cx + sx0 * hl * cs - sy0 * hw * sn; ay = cy + sx0 * hl * sn + sy0 * hw * cs;
             bx = cx + sx1 * hl * cs - sy1 * hw * sn; by = cy + sx1 * hl * sn + sy1 * hw * cs;
             own = o;
-            keep = edge_relevant(ax, ay, bx, by, R2, use_sector, d0, d1, dm);
+            keep = edge_in_disc(ax, ay, bx, by, R2);
           }
         } else {
           const float4 b = reinterpret_cast<const float4*>(k.boundary)[q - n_rect_edges];
           ax = b.x - ex0; ay = b.y - ey0; bx = b.z - ex0; by = b.w - ey0;
           own = FO_HIT_BOUNDARY;
-          keep = edge_relevant(ax, ay, bx, by, R2, use_sector, d0, d1, dm);
+          keep = edge_in_disc(ax, ay, bx, by, R2);
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -149,53 +143,104 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
       }
     }
     __syncthreads();
-    // ---- cast: every lane against every staged edge (shared-memory broadcast) ------------------------
     const int cnt = s_count;
-    if (r < k.n_rays) {
-#pragma unroll 4
-      for (int j = 0; j < cnt; ++j) {
-        const float4 g = sg[j];
-        const float2 t = st[j];
-        const float D = c * g.w - s * g.z;           // cross(d, e)
-        const float un = g.x * s - g.y * c;          // cross(a, d)
-        // t = tn / D >= 0 with tn >= 0, u = un / D in [0, 1], t < best   (division-free, strict improvement only)
-        const bool okk = (D > 0.0f) & (un >= 0.0f) & (un <= D) & (t.x < best * D);
-        if (okk) {
-          best = t.x / D;
-          owner = __float_as_int(t.y);
+
+    // ---- per fan: angular cull of the staged edges into an index list, then cast --------------------------------
+#pragma unroll 1
+    for (int q = 0; q < n_fans; ++q) {
+      const int r_lo = (fan0 + q) * kVisThreads, r_hi = min(r_lo + kVisThreads, k.n_rays) - 1;
+      const int r = r_lo + threadIdx.x;
+      const float span = da * (float)(r_hi - r_lo);
+      const bool use_sector = span < 3.0f;             // fans wider than 180 deg are not culled by angle
+      if (threadIdx.x == 0) s_nfan = 0;
+      __syncthreads();                                 // previous fan's list fully consumed
+      if (use_sector) {
+        float2 d0, d1, dm;
+        sincosf(a0 + da * (float)r_lo - 1e-4f, &d0.y, &d0.x);
+        sincosf(a0 + da * (float)r_hi + 1e-4f, &d1.y, &d1.x);
+        sincosf(a0 + da * 0.5f * (float)(r_lo + r_hi), &dm.y, &dm.x);
+        for (int j0 = 0; j0 < cnt; j0 += kVisThreads) {
+          const int j = j0 + threadIdx.x;
+          bool keep = false;
+          if (j < cnt) {
+            const float4 g = sg[j];
+            keep = edge_in_sector(g.x, g.y, g.x + g.z, g.y + g.w, d0, d1, dm);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          int pos = 0;
+          if (lane == 0 && m) pos = atomicAdd(&s_nfan, __popc(m));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (keep) s_idx[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
         }
+      } else {
+        for (int j = threadIdx.x; j < cnt; j += kVisThreads) s_idx[j] = (uint16_t)j;
+        if (threadIdx.x == 0) s_nfan = cnt;
+      }
+      __syncthreads();
+      const int nf = s_nfan;
+      if (r < k.n_rays) {
+        float c, s;
+        sincosf(a0 + da * (float)r, &s, &c);
+        float bq = R;
+        int oq = FO_HIT_NONE;
+        if (base > 0) { bq = range_f[r]; oq = hit_f[r]; }
+#pragma unroll 4
+        for (int j = 0; j < nf; ++j) {
+          const int e = s_idx[j];
+          const float4 g = sg[e];
+          const float2 t = st[e];
+          const float D = c * g.w - s * g.z;           // cross(d, e)
+          const float un = g.x * s - g.y * c;          // cross(a, d)
+          // t = tn / D >= 0 with tn >= 0, u = un / D in [0, 1], t < best   (division-free, strict improvement only)
+          const bool okk = (D > 0.0f) & (un >= 0.0f) & (un <= D) & (t.x < bq * D);
+          if (okk) {
+            bq = t.x / D;
+            oq = __float_as_int(t.y);
+          }
+        }
+        range_f[r] = bq;
+        hit_f[r] = oq;
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 
-  if (r < k.n_rays) {
-    k.range[(size_t)f * k.n_rays + r] = best;
-    k.hit[(size_t)f * k.n_rays + r] = owner;
+#pragma unroll 1
+  for (int q = 0; q < n_fans; ++q) {
+    const int r = (fan0 + q) * kVisThreads + threadIdx.x;
+    if (r >= k.n_rays) continue;
+    float bq = R;
+    int oq = FO_HIT_NONE;
+    if (n_cand > 0) { bq = range_f[r]; oq = hit_f[r]; }
+    else { range_f[r] = bq; hit_f[r] = oq; }            // no occluder at all: the tile loop never ran
     if (k.visible) {
-      if (owner >= 0) k.visible[(size_t)f * k.n_obstacles + owner] = 1;
+      if (oq >= 0) k.visible[(size_t)f * k.n_obstacles + oq] = 1;
       // transparent obstacles (bicycles): visible when the ray crosses them before its first opaque hit
       const int ntr = s_ntr;
       const bool listed = ntr <= kVisTrCap && k.n_obstacles <= 65535;
       const int n_scan = listed ? ntr : k.n_obstacles;
-      for (int q = 0; q < n_scan; ++q) {
-        const int o = listed ? (int)s_tr[q] : q;
-        const uint8_t fl = flags[o];
-        if ((fl & FO_RECT_EXISTS) && (fl & FO_RECT_TRANSPARENT)) {
-          const float cx = rect[o * 5 + 0] - ex0, cy = rect[o * 5 + 1] - ey0;
-          float sn, cs;
-          sincosf(rect[o * 5 + 2], &sn, &cs);
-          const float hl = rect[o * 5 + 3], hw = rect[o * 5 + 4];
-          // ray vs box in the box frame (slab test)
-          const float ox = -(cx * cs + cy * sn), oy = -(-cx * sn + cy * cs);
-          const float dx = c * cs + s * sn, dy = -c * sn + s * cs;
-          float t0 = 0.0f, t1 = best;
-          bool hitb = true;
-          if (fabsf(dx) > 1e-12f) { float ta = (-hl - ox) / dx, tb = (hl - ox) / dx; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
-          else if (fabsf(ox) > hl) hitb = false;
-          if (fabsf(dy) > 1e-12f) { float ta = (-hw - oy) / dy, tb = (hw - oy) / dy; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
-          else if (fabsf(oy) > hw) hitb = false;
-          if (hitb && t0 <= t1) k.visible[(size_t)f * k.n_obstacles + o] = 1;
+      if (n_scan > 0) {
+        float c, s;
+        sincosf(a0 + da * (float)r, &s, &c);
+        for (int qq = 0; qq < n_scan; ++qq) {
+          const int o = listed ? (int)s_tr[qq] : qq;
+          const uint8_t fl = flags[o];
+          if ((fl & FO_RECT_EXISTS) && (fl & FO_RECT_TRANSPARENT)) {
+            const float cx = rect[o * 5 + 0] - ex0, cy = rect[o * 5 + 1] - ey0;
+            float sn, cs;
+            sincosf(rect[o * 5 + 2], &sn, &cs);
+            const float hl = rect[o * 5 + 3], hw = rect[o * 5 + 4];
+            // ray vs box in the box frame (slab test)
+            const float ox = -(cx * cs + cy * sn), oy = -(-cx * sn + cy * cs);
+            const float dx = c * cs + s * sn, dy = -c * sn + s * cs;
+            float t0 = 0.0f, t1 = bq;
+            bool hitb = true;
+            if (fabsf(dx) > 1e-12f) { float ta = (-hl - ox) / dx, tb = (hl - ox) / dx; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
+            else if (fabsf(ox) > hl) hitb = false;
+            if (fabsf(dy) > 1e-12f) { float ta = (-hw - oy) / dy, tb = (hw - oy) / dy; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
+            else if (fabsf(oy) > hw) hitb = false;
+            if (hitb && t0 <= t1) k.visible[(size_t)f * k.n_obstacles + o] = 1;
+          }
         }
       }
     }
@@ -243,8 +288,16 @@ extern "C" int fo_visibility_raycast(const FoVisibilityArgs* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->visible && a->n_obstacles > 0)
     FO_CUDA_TRY(cudaMemsetAsync(a->visible, 0, (size_t)a->n_frames * a->n_obstacles, st));
-  dim3 grid((a->n_rays + fo::kVisThreads - 1) / fo::kVisThreads, a->n_frames);
-  fo::fo_visibility_kernel<<<grid, fo::kVisThreads, 0, st>>>(*a);
+  // fans per CTA: all of a frame's fans (staging done once per frame) when the frames alone fill the GPU, fewer --
+  // more CTAs per frame -- for the planner's one or two frames
+  const int fans_total = (a->n_rays + fo::kVisThreads - 1) / fo::kVisThreads;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int fpc = fo::kVisFans;
+  while (fpc > 1 && (long long)a->n_frames * ((fans_total + fpc - 1) / fpc) < 4LL * sms) fpc >>= 1;
+  if (fpc > fans_total) fpc = fans_total;
+  dim3 grid((fans_total + fpc - 1) / fpc, a->n_frames);
+  fo::fo_visibility_kernel<<<grid, fo::kVisThreads, 0, st>>>(*a, fpc);
   fo::count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;

@@ -135,11 +135,7 @@ class SensorModel:
                              self.sensor_radius, self.sensor_angle, device=self.device)
 
     def _raycast(self):
-        res = self._frame.raycast(self.n_rays)
-        torch.cuda.current_stream(torch.device(self.device)).synchronize()
-        O = self._frame.n_obstacles
-        return res.range[0].cpu().numpy(), res.hit[0].cpu().numpy(), \
-            (res.visible[0].cpu().numpy() if O else np.zeros(0, np.uint8))
+        return self._frame.raycast_host(self.n_rays)
 
     def _classify(self, points, focus=-1, focus_margin=0.0):
         if self._frame is None:
@@ -173,13 +169,22 @@ class SensorModel:
         # visible obstacles: the reference intersects each obstacle polygon with the (road-clipped) visible area
         # buffered by 1 cm (sensor_model.py:59-76); here: some ray ends on the obstacle at a point of the road
         ang = self.visible_area.angles
+        # ray end points on every seen obstacle, classified in ONE device call
+        ray_lists = [np.nonzero(hit == k)[0] for k in range(O)]
+        need = [k for k in range(O) if bool(vis[k]) and len(ray_lists[k])]
+        on_road = {}
+        if need:
+            rays = np.concatenate([ray_lists[k] for k in need])
+            pts = self.ego_pos + (rng[rays] - 1e-3)[:, None] * np.stack((np.cos(ang[rays]), np.sin(ang[rays])), -1)
+            f, _, _ = self._classify(pts)
+            road = (f & L.PT_ON_ROAD) != 0
+            at = 0
+            for k in need:
+                on_road[k] = bool(road[at:at + len(ray_lists[k])].any())
+                at += len(ray_lists[k])
         for k, o in enumerate(obs):
-            rays = np.nonzero(hit == k)[0]
-            seen = bool(vis[k])
-            if seen and len(rays):
-                pts = self.ego_pos + (rng[rays] - 1e-3)[:, None] * np.stack((np.cos(ang[rays]), np.sin(ang[rays])), -1)
-                f, _, _ = self._classify(pts)
-                seen = bool(np.any(f & L.PT_ON_ROAD))
+            rays = ray_lists[k]
+            seen = on_road[k] if k in on_road else bool(vis[k])
             if seen:
                 self.visible_objects_timestep.append(o.cr_obstacle.obstacle_id)
                 o.current_visible = True

@@ -82,6 +82,25 @@ def raycast_frames(ego, rect, rect_flags, boundary, sensor_radius: float, sensor
     return out
 
 
+_PIN_CACHE = {}
+
+
+def _pinned(nbytes: int):
+    """A reusable page-locked staging buffer of at least ``nbytes`` (uint8) and the event of its last upload."""
+    cap = 1 << max(12, (int(nbytes) - 1).bit_length())
+    ent = _PIN_CACHE.get(cap)
+    if ent is None:
+        ent = [torch.empty(cap, dtype=torch.uint8).pin_memory(), None]
+        _PIN_CACHE[cap] = ent
+    return ent[0], ent[1]
+
+
+def _mark_pinned_in_use(buf: torch.Tensor, device):
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _PIN_CACHE[buf.numel()][1] = ev
+
+
 class FrameGeometry:
     """One sensor frame resident on the device: ego pose, obstacle rectangles, opaque road-border segments and
     the lanelet polygons -- everything ``fo_visibility_raycast`` and ``fo_visibility_points`` read.  All
@@ -109,19 +128,57 @@ class FrameGeometry:
         xy = np.concatenate(polys) if polys else np.zeros((0, 2))
         self.host = {"ego": np.array([0.0, 0.0, self.heading]), "rect": rect, "flags": np.asarray(rect_flags, np.uint8).reshape(-1),
                      "boundary": bnd, "polygons": polys}
+        # ONE packed upload per frame: [ego | rect | boundary | polygon vertices | polygon offsets | flags]
+        def pad4(a):                      # every section starts 16-byte aligned (the kernels load float4 / float2)
+            a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+            return np.concatenate((a, np.zeros((-a.size) % 4, dtype=np.float32)))
+        f32 = [np.array([0.0, 0.0, self.heading, 0.0], dtype=np.float32), pad4(rect), pad4(bnd), pad4(xy)]
+        start = np.concatenate(([0], np.cumsum([a.size for a in f32])))
+        n_f32 = int(start[-1])
+        n_off = len(off) + (-len(off)) % 4
+        total = 4 * n_f32 + 4 * n_off + len(self.host["flags"])
+        host, ev = _pinned(max(total, 64))
+        if ev is not None:
+            ev.synchronize()              # the previous frame's upload from this staging buffer has completed
+        hv = host[:total].numpy()
+        hv[:4 * n_f32].view(np.float32)[:] = np.concatenate(f32)
+        hv[4 * n_f32:4 * (n_f32 + len(off))].view(np.int32)[:] = off
+        hv[4 * (n_f32 + n_off):total] = self.host["flags"]
         with torch.cuda.device(self.device):
-            self.ego_d = torch.tensor([[0.0, 0.0, self.heading]], dtype=torch.float32, device=self.device)
-            self.rect_d = torch.from_numpy(rect.astype(np.float32)).to(self.device)
-            self.flags_d = torch.from_numpy(self.host["flags"].copy()).to(self.device)
-            self.bnd_d = torch.from_numpy(bnd.astype(np.float32)).to(self.device)
-            self.poly_xy_d = torch.from_numpy(xy.astype(np.float32)).to(self.device)
-            self.poly_off_d = torch.from_numpy(off).to(self.device)
+            buf = torch.empty(max(total, 64), dtype=torch.uint8, device=self.device)
+            buf[:total].copy_(host[:total], non_blocking=True)
+            _mark_pinned_in_use(host, self.device)
+            fl = buf[:4 * n_f32].view(torch.float32)
+            self.ego_d = fl[:3].view(1, 3)
+            self.rect_d = fl[start[1]:start[1] + rect.size].view(-1, 5)
+            self.bnd_d = fl[start[2]:start[2] + bnd.size].view(-1, 4)
+            self.poly_xy_d = fl[start[3]:start[3] + xy.size].view(-1, 2)
+            self.poly_off_d = buf[4 * n_f32:4 * (n_f32 + len(off))].view(torch.int32)
+            self.flags_d = buf[4 * (n_f32 + n_off):total]
+            self._buf = buf
+        self._q_in = self._q_out = self._q_host_in = self._q_host_out = None
 
     def raycast(self, n_rays: int) -> VisibilityResult:
         O = self.n_obstacles
         return raycast_frames(self.ego_d, self.rect_d.reshape(1, O, 5), self.flags_d.reshape(1, O),
                               self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg,
                               n_rays, device=self.device)
+
+    def raycast_host(self, n_rays: int):
+        """Ray cast of this frame with ONE packed read-back: host arrays (range f32 [R], hit i32 [R], visible u8 [O])."""
+        O, dev = self.n_obstacles, self.device
+        with torch.cuda.device(dev):
+            nb = 8 * n_rays + max(O, 1)
+            buf = torch.empty(nb, dtype=torch.uint8, device=dev)
+            out = VisibilityResult(buf[:4 * n_rays].view(torch.float32).view(1, n_rays),
+                                   buf[4 * n_rays:8 * n_rays].view(torch.int32).view(1, n_rays),
+                                   buf[8 * n_rays:8 * n_rays + max(O, 1)].view(1, max(O, 1))[:, :O], None, 0.0)
+            raycast_frames(self.ego_d, self.rect_d.reshape(1, O, 5), self.flags_d.reshape(1, O),
+                           self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg, n_rays,
+                           device=dev, out=out)
+            host = buf.cpu().numpy()          # one copy, synchronises
+        return host[:4 * n_rays].view(np.float32), host[4 * n_rays:8 * n_rays].view(np.int32), \
+            (host[8 * n_rays:8 * n_rays + O] if O else np.zeros(0, np.uint8))
 
     def classify(self, points, focus_obstacle: int = -1, focus_margin: float = 0.0):
         """Classify world-frame points [M,2]: returns host arrays (flags uint32, blocker int32, lanelets uint64)."""
@@ -131,10 +188,19 @@ class FrameGeometry:
             return np.zeros(0, np.uint32), np.zeros(0, np.int32), np.zeros(0, np.uint64)
         dev = self.device
         with torch.cuda.device(dev):
-            pts = torch.from_numpy(P.astype(np.float32)).to(dev)
-            flags = torch.empty(M, dtype=torch.int32, device=dev)
-            blocker = torch.empty(M, dtype=torch.int32, device=dev)
-            lan = torch.empty(M, dtype=torch.int64, device=dev)
+            # reusable pinned / device query buffers: one upload, one launch, one packed read-back per call
+            if self._q_in is None or self._q_in.shape[0] < M:
+                cap = max(1024, 1 << (M - 1).bit_length())
+                self._q_in = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+                self._q_out = torch.empty((cap, 4), dtype=torch.int32, device=dev)     # flags | blocker | lanelets (2 words)
+                self._q_host_in = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
+                self._q_host_out = torch.empty((cap, 4), dtype=torch.int32).pin_memory()
+            self._q_host_in[:M].numpy()[:] = P
+            pts = self._q_in[:M]
+            pts.copy_(self._q_host_in[:M], non_blocking=True)
+            res = self._q_out.view(-1)
+            cap = self._q_in.shape[0]
+            flags, blocker, lan = res[:M], res[cap:cap + M], res[2 * cap:2 * cap + 2 * M].view(torch.int64)
             a = L.FoPointQueryArgs()
             a.n_points, a.n_obstacles, a.n_boundary, a.n_polygons = M, self.n_obstacles, self.n_boundary, self.n_polygons
             a.ego, a.points = self.ego_d.data_ptr(), pts.data_ptr()
@@ -147,7 +213,12 @@ class FrameGeometry:
             a.occluded_radius, a.focus_obstacle = self.occluded_radius, int(focus_obstacle)
             a.focus_margin = float(focus_margin)
             a.flags, a.blocker, a.lanelets = flags.data_ptr(), blocker.data_ptr(), lan.data_ptr()
-            L.check(L.lib.fo_visibility_points(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                    "fo_visibility_points")
-            out = (flags.cpu().numpy().view(np.uint32), blocker.cpu().numpy(), lan.cpu().numpy().view(np.uint64))
+            st = torch.cuda.current_stream(dev)
+            L.check(L.lib.fo_visibility_points(C.byref(a), C.c_void_p(st.cuda_stream)), "fo_visibility_points")
+            hout = self._q_host_out.view(-1)
+            n_back = 2 * cap + 2 * M
+            hout[:n_back].copy_(res[:n_back], non_blocking=True)
+            st.synchronize()
+            hn = hout.numpy()
+            out = (hn[:M].view(np.uint32).copy(), hn[cap:cap + M].copy(), hn[2 * cap:2 * cap + 2 * M].view(np.uint64).copy())
         return out
