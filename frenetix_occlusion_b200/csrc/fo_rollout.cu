@@ -14,22 +14,31 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 struct FrenetState { double s, sd, d, dd; };
 
-__device__ __forceinline__ FrenetState frenet_at(double t, double t1, double s0, double v0, double sd1, double d0, double d1) {
+// low_vel: frenetix' low-velocity mode (utils/frenetix_handler.py:91-95, v0 < 0.5 m/s): the lateral quintic runs over the
+// covered ARC LENGTH instead of over time (a vehicle that barely moves cannot shift sideways), d' = dd/ds * ds/dt.
+// Beyond the sampling horizon t1 (real agents: horizon 5 s > t1 = 3 s) the end speed and offset are kept.
+__device__ __forceinline__ FrenetState frenet_at(double t, double t1, double s0, double v0, double sd1, double d0, double d1,
+                                                 bool low_vel) {
   FrenetState f;
+  // quartic: s(0)=s0, s'(0)=v0, s''(0)=0, s'(t1)=sd1, s''(t1)=0
+  const double a3 = (sd1 - v0) / (t1 * t1), a4 = (v0 - sd1) / (2.0 * t1 * t1 * t1);
+  const double s1 = s0 + v0 * t1 + a3 * t1 * t1 * t1 + a4 * t1 * t1 * t1 * t1;
   if (t < t1) {
-    // quartic: s(0)=s0, s'(0)=v0, s''(0)=0, s'(t1)=sd1, s''(t1)=0
-    const double a3 = (sd1 - v0) / (t1 * t1), a4 = (v0 - sd1) / (2.0 * t1 * t1 * t1);
     f.s = s0 + v0 * t + a3 * t * t * t + a4 * t * t * t * t;
     f.sd = v0 + 3.0 * a3 * t * t + 4.0 * a4 * t * t * t;
-    // quintic: d(0)=d0, d'(0)=d''(0)=0, d(t1)=d1, d'(t1)=d''(t1)=0
-    const double tau = t / t1, t2 = tau * tau, t3 = t2 * tau;
-    f.d = d0 + (d1 - d0) * (10.0 * t3 - 15.0 * t3 * tau + 6.0 * t3 * t2);
-    f.dd = (d1 - d0) / t1 * (30.0 * t2 - 60.0 * t3 + 30.0 * t2 * t2);
-  } else {   // beyond the sampling horizon: keep the end speed and offset
-    const double a3 = (sd1 - v0) / (t1 * t1), a4 = (v0 - sd1) / (2.0 * t1 * t1 * t1);
-    const double s1 = s0 + v0 * t1 + a3 * t1 * t1 * t1 + a4 * t1 * t1 * t1 * t1;
+  } else {
     f.s = s1 + sd1 * (t - t1);
     f.sd = sd1;
+  }
+  if (t < t1 || low_vel) {
+    // quintic: d(0)=d0, d'(0)=d''(0)=0, d(end)=d1, d'(end)=d''(end)=0 over time, or over arc length in low_vel mode
+    // (there d follows the covered arc length at every t: an agent that has not moved has not shifted sideways)
+    const double span = low_vel ? fmax(s1 - s0, 1e-9) : t1;
+    const double tau = low_vel ? fmin(fmax((f.s - s0) / span, 0.0), 1.0) : t / t1;
+    const double t2 = tau * tau, t3 = t2 * tau;
+    f.d = d0 + (d1 - d0) * (10.0 * t3 - 15.0 * t3 * tau + 6.0 * t3 * t2);
+    f.dd = (d1 - d0) / span * (30.0 * t2 - 60.0 * t3 + 30.0 * t2 * t2) * (low_vel ? f.sd : 1.0);
+  } else {
     f.d = d1;
     f.dd = 0.0;
   }
@@ -92,6 +101,7 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
     if (ob < best || (ob == best && os < bs)) { best = ob; bs = os; bd = od; }
   }
   const double s0 = bs, d0 = bd;
+  const bool low_vel = v0 < 0.5;                        // frenetix_handler.py:91-95
 
   // ---- 3 x 3 samples: variance of the Cartesian speed over the horizon -----------------------------------
   const int T = k.n_states;
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
     const double sd1 = v0 * (0.8 + 0.2 * (double)(smp / 3)), d1 = -0.5 + 0.5 * (double)(smp % 3);
     double sum = 0.0, sq = 0.0;
     for (int i = lane; i < T; i += 32) {
-      const FrenetState f = frenet_at((double)i * k.dt, k.t1, s0, v0, sd1, d0, d1);
+      const FrenetState f = frenet_at((double)i * k.dt, k.t1, s0, v0, sd1, d0, d1, low_vel);
       const int j = seg_of(cum, np, f.s);
       // curvature of the polyline at segment j: heading change to the next segment over the mean length
       double kap = 0.0;
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
   for (int i = lane; i < k.t_stride; i += 32) {
     float ox = 0, oy = 0, oyaw = 0, ov = 0, ovar = 0;
     if (i < T) {
-      const FrenetState f = frenet_at((double)i * k.dt, k.t1, s0, v0, sd1, d0, d1);
+      const FrenetState f = frenet_at((double)i * k.dt, k.t1, s0, v0, sd1, d0, d1, low_vel);
       const int j = seg_of(cum, np, f.s);
       const double ax = pts[j].x, ay = pts[j].y, ex = pts[j + 1].x - ax, ey = pts[j + 1].y - ay;
       const double l = fmax(cum[j + 1] - cum[j], 1e-12);

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   __shared__ float4 sg[kVisTile];       // a.x, a.y, e.x, e.y of the staged (disc-culled, oriented) edges
   __shared__ float2 st[kVisTile];       // (cross(a, e), owner as int bits)
   __shared__ uint16_t s_idx[kVisTile];  // staged edges that touch the current fan's sector
-  __shared__ int s_count, s_nfan;
+  __shared__ int s_count, s_nfan[2];    // s_nfan alternates between fans: the reset of one never races the readers of the other
   __shared__ int s_ntr;                 // transparent (bicycle) obstacles of this frame
   __shared__ uint16_t s_tr[kVisTrCap];
   const int f = blockIdx.y;
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
       const int r = r_lo + threadIdx.x;
       const float span = da * (float)(r_hi - r_lo);
       const bool use_sector = span < 3.0f;             // fans wider than 180 deg are not culled by angle
-      if (threadIdx.x == 0) s_nfan = 0;
-      __syncthreads();                                 // previous fan's list fully consumed
+      int* const nfan = &s_nfan[q & 1];
+      if (threadIdx.x == 0) *nfan = 0;
+      __syncthreads();                                 // previous fan's list fully consumed (its counter is the other slot)
       if (use_sector) {
         float2 d0, d1, dm;
         sincosf(a0 + da * (float)r_lo - 1e-4f, &d0.y, &d0.x);
@@ -168,16 +169,16 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
           }
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           int pos = 0;
-          if (lane == 0 && m) pos = atomicAdd(&s_nfan, __popc(m));
+          if (lane == 0 && m) pos = atomicAdd(nfan, __popc(m));
           pos = __shfl_sync(0xffffffffu, pos, 0);
           if (keep) s_idx[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
         }
       } else {
         for (int j = threadIdx.x; j < cnt; j += kVisThreads) s_idx[j] = (uint16_t)j;
-        if (threadIdx.x == 0) s_nfan = cnt;
+        if (threadIdx.x == 0) *nfan = cnt;
       }
       __syncthreads();
-      const int nf = s_nfan;
+      const int nf = *nfan;
       if (r < k.n_rays) {
         float c, s;
         sincosf(a0 + da * (float)r, &s, &c);

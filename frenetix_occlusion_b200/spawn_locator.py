@@ -237,8 +237,10 @@ class SpawnLocator:
         P = np.stack((center[0] + gx.ravel() * cs - gy.ravel() * sn, center[1] + gx.ravel() * sn + gy.ravel() * cs), -1)
         inside = self._region_predicate(P, dyn_obst, possible_ids, opposite)
         # restrict to the selected connected part of the allowed area (coarse raster, one cell of slack)
-        from scipy import ndimage
-        comp = ndimage.binary_dilation(region["mask"], iterations=1)
+        if "mask_dilated" not in region:
+            from scipy import ndimage
+            region["mask_dilated"] = ndimage.binary_dilation(region["mask"], iterations=1)
+        comp = region["mask_dilated"]
         ij = np.floor((P - region["origin"]) / self.raster_cell).astype(int)
         ok = (ij[:, 0] >= 0) & (ij[:, 0] < region["n"]) & (ij[:, 1] >= 0) & (ij[:, 1] < region["n"])
         sel = np.zeros(len(P), dtype=bool)
@@ -248,7 +250,11 @@ class SpawnLocator:
         if inside.sum() < 3:
             return {"area": area, "area_ratio": 0.0, "jaccard_similarity": 0.0, "centroid": np.asarray(center, float)}
         pts = P[inside]
-        _, w, h, ang = hf.min_area_rectangle(pts)
+        # the minimum rotated rectangle only depends on the outline: cells with a missing 4-neighbour
+        m = inside.reshape(nx, ny)
+        pad = np.pad(m, 1)
+        core = pad[:-2, 1:-1] & pad[2:, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:]
+        _, w, h, ang = hf.min_area_rectangle(P[(m & ~core).ravel()])
         # the samples are cell centres: the covered set extends half a cell beyond them on every side
         grow = c * (abs(np.cos(ang - orientation)) + abs(np.sin(ang - orientation)))
         mbr_area = (w + grow) * (h + grow)

@@ -374,7 +374,7 @@ class TrajectoryHandler:
                 # low-velocity mode: the lateral offset is a function of the covered arc length, not of time
                 s_end = float(_quartic(np.array([t1]), t0, t1, s0, ss0, sss0, ss1, sss1)[0][0])
                 span = max(s_end - s0, 1e-9)
-                d, dprime = _quintic(s - s0, 0.0, span, d0, dd0, ddd0, d1, dd1, ddd1)
+                d, dprime = _quintic(np.clip(s - s0, 0.0, span), 0.0, span, d0, dd0, ddd0, d1, dd1, ddd1)
                 dd = dprime * sd
             else:
                 d, dd = _quintic(t, t0, t1, d0, dd0, ddd0, d1, dd1, ddd1)

@@ -213,9 +213,17 @@ def rollout_path(path, x0, y0, v0, dt, horizon, t1=3.0, var0=0.1, var_factor=1.0
         tc = np.minimum(t, t1)
         s = s0 + v0 * tc + a3 * tc ** 3 + a4 * tc ** 4 + np.where(t > t1, sd1 * (t - t1), 0.0)
         sd = np.where(t < t1, v0 + 3 * a3 * tc ** 2 + 4 * a4 * tc ** 3, sd1)
-        tau = tc / t1
-        d = np.where(t < t1, d0 + (d1 - d0) * (10 * tau ** 3 - 15 * tau ** 4 + 6 * tau ** 5), d1)
-        dd = np.where(t < t1, (d1 - d0) / t1 * (30 * tau ** 2 - 60 * tau ** 3 + 30 * tau ** 4), 0.0)
+        if v0 < 0.5:                     # low-velocity mode (frenetix_handler.py:91-95): lateral quintic over arc length
+            s1 = s0 + v0 * t1 + a3 * t1 ** 3 + a4 * t1 ** 4
+            span = max(s1 - s0, 1e-9)
+            tau = np.clip((s - s0) / span, 0.0, 1.0)
+            scale = sd / span
+        else:
+            tau = tc / t1
+            scale = 1.0 / t1
+        inside = (t < t1) | (v0 < 0.5)   # low-velocity mode: d follows the covered arc length at every t
+        d = np.where(inside, d0 + (d1 - d0) * (10 * tau ** 3 - 15 * tau ** 4 + 6 * tau ** 5), d1)
+        dd = np.where(inside, (d1 - d0) * scale * (30 * tau ** 2 - 60 * tau ** 3 + 30 * tau ** 4), 0.0)
         return s, sd, d, dd
 
     def lookup(s):

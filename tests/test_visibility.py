@@ -139,6 +139,12 @@ def test_path_rollout_oracle_invariants():
     r = VO.rollout_path(arc, arc[10, 0], arc[10, 1], 8.0, 0.1, 3.0)
     rad = np.hypot(r["x"], r["y"] - 40.0)
     assert np.all(np.abs(rad - 40.0) < 0.01)
+    # low-velocity mode (v0 < 0.5 m/s, frenetix_handler.py:91-95): the lateral offset is a function of the covered arc
+    # length -- an agent that stands still (v0 = 0: every sample has end speed 0) does not move sideways either
+    r = VO.rollout_path(path, 5.0, 0.4, 0.0, 0.1, 3.0)
+    assert np.allclose(r["x"], 5.0) and np.allclose(r["y"], 0.4) and np.allclose(r["v"], 0.0)
+    r = VO.rollout_path(path, 5.0, 0.4, 0.3, 0.1, 3.0)
+    assert abs(r["y"][0] - 0.4) < 1e-12 and np.all(np.diff(r["x"]) > 0) and np.all(np.abs(r["y"] - 0.4) <= 0.9 + 1e-9)
 
 
 @pytest.mark.gpu
@@ -148,9 +154,10 @@ def test_cuda_path_rollout_matches_oracle(cuda_device):
     rng = np.random.default_rng(8)
     paths = [np.stack((np.linspace(-10, 100, 56), np.zeros(56)), -1), _arc_path(40.0), _arc_path(-25.0, 300, 150.0),
              np.stack((np.linspace(0, 60, 31), 3.0 * np.sin(np.linspace(0, 60, 31) / 9.0)), -1)]
-    x0 = [5.0, 9.0, 3.0, 12.0]
-    y0 = [0.4, 1.5, -0.3, 2.2]
-    v0 = [10.0, 8.0, 5.0, 10.0]
+    paths.append(paths[0])                                  # low-velocity mode: v0 < 0.5 m/s
+    x0 = [5.0, 9.0, 3.0, 12.0, 7.0]
+    y0 = [0.4, 1.5, -0.3, 2.2, 0.3]
+    v0 = [10.0, 8.0, 5.0, 10.0, 0.3]
     for horizon in (3.0, 5.0):
         g = rollout_path(paths, x0, y0, v0, 0.1, horizon)
         torch.cuda.synchronize()
