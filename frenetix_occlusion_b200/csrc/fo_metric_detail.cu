@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
     }
     __syncwarp();
     float be_lo0 = 0.0f;
+    bool be_ready = false;                                                       // arc-length table built on first use
     if (do_be && do_ttc) {
-      be_prepare(bev, T, lane);                                                  // arc length + bucket table, be.py:99
       const float am = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fabsf(amin))));   // |min(min a, 0)|, be.py:68 (amin <= 0)
       be_lo0 = rintf(am * 100.0f) / 100.0f;
     }
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
 
       // ---- pre-pass: min over time of the squared centre distance = upper bound of the pair's minimum distance --
       float U2 = CUDART_INF_F;
+      int i_star = -1;                                   // step of the smallest centre distance
       if (do_dce) {
         const int nAmax = (int)__reduce_max_sync(kFull, (unsigned)nA);
         const float4* t0p = k.tab.t0 + a;
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
             const float4 s0 = __ldg(t0p);
             const float4 EA = egoA[i];
             const float dx = fmaf(-k.wb, EA.z, s0.x - EA.x), dy = fmaf(-k.wb, EA.w, s0.y - EA.y);
-            U2 = fminf(U2, fmaf(dx, dx, dy * dy));
+            const float c2 = fmaf(dx, dx, dy * dy);
+            if (c2 < U2) { U2 = c2; i_star = i; }
           }
         }
       }
@@ -327,9 +329,21 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
         }
       };
 
+      // The step of the closest centres is queued FIRST: its exact distance is, or is close to, the pair's minimum, so
+      // after the first drain (a full one for a full tile, at the top of the step loop) the bound is tight instead of
+      // starting at the centre distance.
+      int qn = 0;
+      if (do_dce) {
+        const bool has = i_star >= 0;
+        const unsigned b = __ballot_sync(kFull, has);
+        if (has) q_near[__popc(b & lt_mask)] = ((uint32_t)lane << 8) | (uint32_t)i_star;
+        qn = __popc(b);
+        __syncwarp();
+      }
+
       // ---- the step loop: lane = agent, i = state index ----------------------------------------------------------
       float eh_m = 0.0f, oh_m = 0.0f;
-      int qn = 0, qc = 0;
+      int qc = 0;
       float pxp = 0.0f, pyp = 0.0f;                      // position at i-1 (collision_probability.py:52)
       const float hlb2 = P.hlb * P.hlb, hlbm2 = -2.0f * P.hlb;
       const uint32_t item0 = (uint32_t)lane << 8;
@@ -351,9 +365,9 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
         const float c = fmaf(EA.z, s0.z, EA.w * s0.w);                                // cos(yaw - theta)
         if (do_dce) {
           const float dx = fmaf(-k.wb, EA.z, dxr), dy = fmaf(-k.wb, EA.w, dyr);       // centre to centre
-          const bool need = liveA & (fmaf(dx, dx, dy * dy) < lim2);
+          const bool need = liveA & (fmaf(dx, dx, dy * dy) < lim2) & (i != i_star);
           const unsigned b = __ballot_sync(kFull, need);
-          if (b || last) {
+          if (b || last || qn >= 32) {
             if (need) q_near[qn + __popc(b & lt_mask)] = item0 | (uint32_t)i;
             qn += __popc(b);
             __syncwarp();
@@ -434,6 +448,7 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
       float rcd = 0.0f, btn = 0.0f;
       if (do_be && do_ttc) {
         unsigned todo = __ballot_sync(kFull, collides && t_col > 0);
+        if (todo && !be_ready) { be_prepare(bev, T, lane); be_ready = true; }    // arc length + bucket table, be.py:99
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;

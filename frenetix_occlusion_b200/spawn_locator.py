@@ -420,16 +420,23 @@ class SpawnLocator:
         # walk s in +0.5 m steps until a 0.5 m disc no longer touches the visible area (spawn_locator.py:552-554);
         # the candidate discs are classified in batches of 32 steps (one device call each) instead of one by one
         phantom_pos = None
+        vec = getattr(self.cosy_cl, "convert_array_to_cartesian_coords", None)
         for k0 in range(0, 416, 32):
-            cand = []
-            for k in range(k0, k0 + 32):
-                try:
-                    cand.append(np.asarray(self.cosy_cl.convert_to_cartesian_coords(s_phantom + 0.5 * k, d_offset)))
-                except Exception:
-                    break           # the reference raises out of the coordinate system here
-            if not cand:
+            if vec is not None:          # vectorised conversion (the harness' coordinate system); NaN = outside the path
+                cand = vec(s_phantom + 0.5 * np.arange(k0, k0 + 32), d_offset)
+                bad = np.nonzero(np.isnan(cand[:, 0]))[0]
+                cand = cand[:int(bad[0])] if len(bad) else cand
+            else:
+                cand = []
+                for k in range(k0, k0 + 32):
+                    try:
+                        cand.append(np.asarray(self.cosy_cl.convert_to_cartesian_coords(s_phantom + 0.5 * k, d_offset)))
+                    except Exception:
+                        break           # the reference raises out of the coordinate system here
+                cand = np.asarray(cand, dtype=np.float64).reshape(-1, 2)
+            if not len(cand):
                 return
-            discs = np.concatenate([hf.disc_samples(c, 0.5) for c in cand])
+            discs = hf.disc_samples_many(cand, 0.5).reshape(-1, 2)
             vis = np.atleast_1d(self.sensor_model.visible_area.contains(discs)).reshape(len(cand), -1).any(1)
             free = np.nonzero(~vis)[0]
             if len(free):
@@ -488,6 +495,13 @@ class SpawnLocator:
                 self.spawn_points.append(spawn_point)
 
     def _convert_curvilinear_list_to_cartesian_coordinates(self, curvilinear_list):
+        vec = getattr(self.cosy_cl, "convert_array_to_cartesian_coords", None)
+        if vec is not None:
+            cl = np.asarray(curvilinear_list, dtype=np.float64).reshape(-1, 2)
+            out = vec(cl[:, 0], cl[:, 1])
+            if np.isnan(out).any():
+                raise ValueError("longitudinal coordinate outside of the reference path")
+            return out
         return np.array([self.cosy_cl.convert_to_cartesian_coords(item[0], item[1]) for item in curvilinear_list])
 
     def _find_orientation_at_position(self, pos):

@@ -54,6 +54,16 @@ class CurvilinearCoordinateSystem:
         j = int(np.clip(np.searchsorted(self._s, s, side="right") - 1, 0, len(self._len) - 1))
         return self._p[j] + (s - self._s[j]) * self._t[j] + float(d) * self._n[j]
 
+    def convert_array_to_cartesian_coords(self, s, d):
+        """Vectorised ``convert_to_cartesian_coords`` (extension used by the spawn locator when available): rows whose
+        longitudinal coordinate lies outside the path are NaN."""
+        s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+        d = np.broadcast_to(np.asarray(d, dtype=np.float64), s.shape)
+        j = np.clip(np.searchsorted(self._s, s, side="right") - 1, 0, len(self._len) - 1)
+        out = self._p[j] + (s - self._s[j])[:, None] * self._t[j] + d[:, None] * self._n[j]
+        out[(s < -self._eps) | (s > self._s[-1] + self._eps)] = np.nan
+        return out
+
     def convert_list_of_points_to_curvilinear_coords(self, points, num_omp_threads=1):
         out = []
         for p in points:

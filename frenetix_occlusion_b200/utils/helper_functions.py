@@ -102,6 +102,15 @@ def disc_samples(center, radius, n_rim=32, n_rings=3) -> np.ndarray:
     return np.concatenate(pts)
 
 
+def disc_samples_many(centers, radius, n_rim=32, n_rings=3) -> np.ndarray:
+    """``disc_samples`` for K centres at once: [K, 1 + n_rim * n_rings, 2], same sample order per disc."""
+    c = np.asarray(centers, dtype=np.float64).reshape(-1, 2)
+    ang = np.linspace(0.0, 2.0 * np.pi, n_rim, endpoint=False)
+    unit = np.stack((np.cos(ang), np.sin(ang)), -1)
+    offs = np.concatenate([np.zeros((1, 2))] + [radius * k / n_rings * unit for k in range(1, n_rings + 1)])
+    return c[:, None, :] + offs[None, :, :]
+
+
 def min_area_rectangle(points):
     """Minimum rotated bounding rectangle of a point set: (area, width, height, angle) by rotating calipers
     over the convex hull edges (shapely ``minimum_rotated_rectangle`` semantics)."""
