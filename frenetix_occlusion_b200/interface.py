@@ -24,7 +24,7 @@ from .utils.fo_obstacle import FOObstacles
 
 class FOInterface:
     def __init__(self, scenario, reference_path, vehicle_params, dt, config_path=None, cosy_cl=None, device="cuda:0",
-                 visualization=None):
+                 visualization=None, warm_up=True):
         self.config = self._load_config(config_path)
         self.cr_scenario = scenario
         self.lanelet_network = scenario.lanelet_network
@@ -58,6 +58,8 @@ class FOInterface:
                                           fo_obstacles=self.fo_obstacles, visualization=self.visualization,
                                           debug=self.debug)
         self.metrics = self._make_metrics()
+        if warm_up:
+            self._warm_up()
 
     # construction hooks (one per device-backed component)
     def _make_sensor_model(self):
@@ -73,6 +75,38 @@ class FOInterface:
 
     def _make_metrics(self):
         return Metric(self.config["metrics"], self.vehicle_params, self.agent_manager, device=self.device)
+
+    def _warm_up(self):
+        """Pay the first-use costs (CUDA context, module load, page-locked staging buffers, kernel attributes) at
+        construction instead of in the first planning cycle: one tiny call of every device entry point."""
+        import numpy as np
+        import torch
+        from .engine import AgentSet
+        from .prediction import rollout_cv, rollout_path
+        from .visibility import FrameGeometry
+        if not torch.cuda.is_available() or not hasattr(self.sensor_model, "n_rays"):
+            return
+        road = [np.array([[-1.0, -2.0], [30.0, -2.0], [30.0, 4.0], [-1.0, 4.0]])]
+        fr = FrameGeometry([0.0, 0.0], 0.0, np.array([[8.0, 0.5, 0.1, 2.0, 1.0]]), np.array([1], dtype=np.uint8),
+                           np.array([[0.0, 4.0, 30.0, 4.0]]), road, self.sensor_radius, self.sensor_angle, device=self.device)
+        fr.raycast_host(self.sensor_model.n_rays)
+        fr.classify(np.array([[3.0, 1.0], [15.0, 0.5]]), focus_obstacle=0, focus_margin=1.0)
+        rollout_cv([1.0], [1.0], [1.4], [0.3], self.dt, 3.0, device=self.device)
+        rollout_path([np.array([[0.0, 0.0], [20.0, 0.0], [40.0, 1.0]])], [2.0], [0.2], [5.0], self.dt, 3.0, device=self.device)
+        core = getattr(self.metrics, "_core", None)
+        if core is not None:
+            n = int(round(3.0 / self.dt)) + 1
+            t = np.arange(n) * self.dt
+            agent = {"agent_type": "Pedestrian", "length": 0.3, "width": 0.5, "buf_length": 0.36, "buf_width": 0.65,
+                     "pos": np.stack((12.0 + 0 * t, -3.0 + 1.4 * t), -1), "yaw": np.full(n, 1.57), "v": np.full(n, 1.4),
+                     "var": 0.1 * 1.05 ** np.arange(n)}
+            ego = np.stack((8.0 * t, 0 * t, 0 * t, 8.0 + 0 * t, 0 * t), -1)[None]
+            core.engine.set_agents(AgentSet.from_case([agent]))
+            core.engine.assess(ego)                                       # summary kernel
+            core.engine.assess(ego, want_pair=True, want_step=True)       # detail kernel
+            core.engine.set_agents(AgentSet.from_case([]))
+            core._fingerprint = None
+        torch.cuda.current_stream(torch.device(self.device)).synchronize()
 
     def set_coordinate_system(self, cosy_cl):
         self.cosy_cl = cosy_cl

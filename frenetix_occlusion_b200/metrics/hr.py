@@ -41,8 +41,8 @@ class HR:
             eh = np.array(d["step"][k, :P, 1])
             oh = np.array(d["step"][k, :P, 2])
             c = np.asarray(cp[pid], dtype=np.float64)
-            er = [eh[t] * c[t] for t in range(P)]           # hr.py:78-79
-            orr = [oh[t] * c[t] for t in range(P)]
+            er = list(eh * c[:P])                           # hr.py:78-79 (lists of numpy floats, as the reference builds)
+            orr = list(oh * c[:P])
             p = d["pair"][k]
             out[pid] = {"max_ego_risk": p[2], "max_obst_risk": p[3], "max_obst_harm_with_cp": p[5],
                         "max_obst_risk_index": int(p[4]), "max_ego_harm": p[6], "max_obst_harm": p[7],
