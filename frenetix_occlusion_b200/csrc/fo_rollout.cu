@@ -58,6 +58,7 @@ __device__ __forceinline__ int seg_of(const double* cum, int np, double s) {
 __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPathArgs k) {
   __shared__ double cum[kMaxPathPts];      // arc length at every vertex
   __shared__ float2 pts[kMaxPathPts];
+  __shared__ double head[kMaxPathPts];     // heading of segment j (vertex j -> j + 1)
   const int job = blockIdx.x, lane = threadIdx.x;
   const int off = k.path_off[job], np = min(k.path_off[job + 1] - off, kMaxPathPts);
   const size_t row = (size_t)job * k.t_stride;
@@ -68,14 +69,22 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
   }
   for (int j = lane; j < np; j += 32) pts[j] = reinterpret_cast<const float2*>(k.path_xy)[off + j];
   __syncwarp();
-  if (lane == 0) {   // sequential prefix sum (np <= 1024, once per job)
-    double acc = 0.0;
-    cum[0] = 0.0;
-    for (int j = 1; j < np; ++j) {
-      acc += hypot((double)pts[j].x - pts[j - 1].x, (double)pts[j].y - pts[j - 1].y);
-      cum[j] = acc;
+  {   // arc length at every vertex: warp scan over chunks of 32 chords (a route path has up to 1024 vertices)
+    double carry = 0.0;
+    for (int j0 = 0; j0 < np; j0 += 32) {
+      const int j = j0 + lane;
+      double sc = (j >= 1 && j < np) ? hypot((double)pts[j].x - pts[j - 1].x, (double)pts[j].y - pts[j - 1].y) : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, sc, o);
+        if (lane >= o) sc += t;
+      }
+      if (j < np) cum[j] = carry + sc;
+      carry += __shfl_sync(kFullMask, sc, 31);
     }
   }
+  for (int j = lane; j < np - 1; j += 32)
+    head[j] = atan2((double)pts[j + 1].y - pts[j].y, (double)pts[j + 1].x - pts[j].x);
   __syncwarp();
 
   // ---- projection of the start position: closest point over all segments -> (s0, d0) -----------------
@@ -116,9 +125,7 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
       // curvature of the polyline at segment j: heading change to the next segment over the mean length
       double kap = 0.0;
       if (j + 2 < np) {
-        const double h0 = atan2((double)pts[j + 1].y - pts[j].y, (double)pts[j + 1].x - pts[j].x);
-        const double h1 = atan2((double)pts[j + 2].y - pts[j + 1].y, (double)pts[j + 2].x - pts[j + 1].x);
-        double dh = h1 - h0;
+        double dh = head[j + 1] - head[j];
         dh -= 2.0 * CUDART_PI * rint(dh / (2.0 * CUDART_PI));
         kap = dh / (0.5 * (cum[j + 2] - cum[j]));
       }
@@ -146,16 +153,14 @@ __global__ void __launch_bounds__(32) fo_rollout_path_kernel(const FoRolloutPath
       const double tx = ex / l, ty = ey / l;
       double kap = 0.0;
       if (j + 2 < np) {
-        const double h0 = atan2(ey, ex);
-        const double h1 = atan2((double)pts[j + 2].y - pts[j + 1].y, (double)pts[j + 2].x - pts[j + 1].x);
-        double dh = h1 - h0;
+        double dh = head[j + 1] - head[j];
         dh -= 2.0 * CUDART_PI * rint(dh / (2.0 * CUDART_PI));
         kap = dh / (0.5 * (cum[j + 2] - cum[j]));
       }
       const double vl = f.sd * (1.0 - kap * f.d);
       ox = (float)(ax + u * ex - f.d * ty);
       oy = (float)(ay + u * ey + f.d * tx);
-      oyaw = (float)(atan2(ty, tx) + atan2(f.dd, vl));
+      oyaw = (float)(head[j] + atan2(f.dd, vl));
       ov = (float)sqrt(vl * vl + f.dd * f.dd);
       ovar = (float)(k.var0 * pow(k.var_factor, (double)i));
     }

@@ -80,6 +80,7 @@ class FOInterface:
         """Pay the first-use costs (CUDA context, module load, page-locked staging buffers, kernel attributes) at
         construction instead of in the first planning cycle: one tiny call of every device entry point."""
         import numpy as np
+        import scipy.ndimage  # noqa: F401  (the spawn locator's first use would otherwise pay the import in cycle 0)
         import torch
         from .engine import AgentSet
         from .prediction import rollout_cv, rollout_path
