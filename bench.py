@@ -583,48 +583,29 @@ def run_stages(dev, hbm_peak=6650.0, hbm_src="of fallback 6.65 TB/s", fp32_peak=
         ts.append(a.elapsed_time(b))
     ms = float(np.mean(ts))
     tests = F * R * 4 * O
-    # executed ray x edge tests: the kernel's two culls (sensor disc per frame, angular sector per 256-ray fan) replayed
-    # in numpy on a sample of frames
-    def executed_tests(rect_h, n_sample=16):
-        tot = 0
-        for f in range(n_sample):
-            r = rect_h[f].astype(np.float64)
-            cs, sn = np.cos(r[:, 2]), np.sin(r[:, 2])
-            sx = np.array([-1, -1, 1, 1.0]); sy = np.array([-1, 1, 1, -1.0])
-            cx = r[:, 0, None] + sx * r[:, 3, None] * cs[:, None] - sy * r[:, 4, None] * sn[:, None]
-            cy = r[:, 1, None] + sx * r[:, 3, None] * sn[:, None] + sy * r[:, 4, None] * cs[:, None]
-            a = np.stack((cx, cy), -1).reshape(-1, 2)                                  # corner k of every rectangle
-            b = np.stack((np.roll(cx, -1, 1), np.roll(cy, -1, 1)), -1).reshape(-1, 2)  # corner k + 1
-            e = b - a
-            t = np.clip(-(a * e).sum(1) / np.maximum((e * e).sum(1), 1e-30), 0, 1)
-            p = a + t[:, None] * e
-            keep = (p * p).sum(1) <= 50.0 ** 2
-            a, b = a[keep], b[keep]
-            n_fans = R // 256
-            for q in range(n_fans):
-                lo, hi = -np.pi + 2 * np.pi * (q * 256) / R - 1e-4, -np.pi + 2 * np.pi * (q * 256 + 255) / R + 1e-4
-                d0, d1 = np.array([np.cos(lo), np.sin(lo)]), np.array([np.cos(hi), np.sin(hi)])
-                dm = np.array([np.cos(0.5 * (lo + hi)), np.sin(0.5 * (lo + hi))])
-                c0a, c0b = d0[0] * a[:, 1] - d0[1] * a[:, 0], d0[0] * b[:, 1] - d0[1] * b[:, 0]
-                c1a, c1b = a[:, 0] * d1[1] - a[:, 1] * d1[0], b[:, 0] * d1[1] - b[:, 1] * d1[0]
-                out = ((c0a < 0) & (c0b < 0)) | ((c1a < 0) & (c1b < 0)) | (((a @ dm) < 0) & ((b @ dm) < 0))
-                tot += int((~out).sum()) * 256
-        return tot / n_sample
-    exec_tests = executed_tests(rect[:16].cpu().numpy()) * F
+    # executed work: the instrumented twin of the kernel (fo_visibility_stats) counts what survives the culls
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+    raycast_frames(ego, rect, flags, None, 50.0, 360.0, R, device=dev, out=res, stats=cnt)
+    torch.cuda.synchronize()
+    exec_tests, skipped, staged, listed = (float(v) for v in cnt.cpu().tolist())
+    # instruction model of the cast: ~18 issue slots per executed test (2 LDS.128/64, 6 FP32, 4 compares, vote, loop),
+    # ~5 per skipped (warp, edge) pair; 10 flop per executed test
     out["visibility"] = {"workload": "C-vis 10000 frames x 4096 rays x 512 rectangles", "kernel_ms": ms,
                          "frames_per_s": F / (ms * 1e-3), "ray_edge_tests_per_s": tests / (ms * 1e-3),
                          "roofline": {"bound": "fp32", "kernel": "fo_visibility_kernel", "unit": "TFLOP/s",
-                                      # 9 instructions / ~10 flop per executed ray x staged-edge test
                                       "achieved": exec_tests * 10 / (ms * 1e-3) / 1e12, "peak": fp32_peak,
                                       "frac": exec_tests * 10 / (ms * 1e-3) / 1e12 / fp32_peak, "peak_source": fp32_src,
                                       "executed_tests_per_frame": exec_tests / F, "brute_force_tests_per_frame": tests / F,
+                                      "skipped_warp_edge_pairs_per_frame": skipped / F, "staged_edges_per_frame": staged / F,
+                                      "fan_list_entries_per_frame": listed / F,
                                       "effective_achieved": tests * 20 / (ms * 1e-3) / 1e12,
                                       "effective_frac": tests * 20 / (ms * 1e-3) / 1e12 / fp32_peak,
-                                      "note": "frac: tests the kernel executes after its disc / per-fan sector culls (replayed "
-                                              "on 16 sample frames), 10 flop each; effective_frac: SURVEY.md 8d's algorithmic "
-                                              "20 flop per brute-force ray x edge test -- it measures the culling.  ncu: issue "
-                                              "slots 91 % busy, 30.7 of 32 lanes (profiles/ncu_r2_visibility_summary.txt): the "
-                                              "kernel is issue-bound on the cast loop, not FP32-bound",
+                                      "note": "frac: ray x edge tests the kernel really executes (counted by its instrumented "
+                                              "twin, fo_visibility_stats: after the sensor-disc cull, the per-fan sector cull and "
+                                              "the near-to-far skip of edges beyond the warp's farthest hit), 10 flop each; "
+                                              "effective_frac: SURVEY.md 8d's algorithmic 20 flop per brute-force ray x edge test "
+                                              "-- it measures the culling, not the pipes.  The kernel is issue-bound, not "
+                                              "FP32-bound (profiles/ncu_r2_visibility_summary.txt)",
                                       "hbm_frac": F * (O * 21 + R * 8 + O) / (ms * 1e-3) / 1e9 / hbm_peak,
                                       "algorithmic_bytes": F * (O * 21 + R * 8 + O)}}
     # the same frames with a 400-segment road-border ring (real scenes always have one: 350-400 border edges)

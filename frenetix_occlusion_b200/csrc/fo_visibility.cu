@@ -2,12 +2,17 @@
 //
 // One CTA = 8 warps owns up to 16 fans of 256 consecutive rays of one frame (all 4096 rays of a frame when the call
 // has enough frames to fill the GPU; fewer fans per CTA -- more CTAs per frame -- for the planner's single frame);
-// one lane = one ray per fan, its running first hit lives in registers across the fans' turns.  The frame's occluder
-// edges (4 per obstacle rectangle + shared road-border segments) are transformed into the ego frame, culled against the
-// sensor disc, oriented and compacted into shared memory ONCE per CTA (the transform costs a sincosf per rectangle
-// edge; round 1 redid it for every 256-ray fan); per fan the staged edges are culled against the fan's angular
-// sector into a shared index list, and every lane walks that list (all lanes read the same shared-memory word:
-// broadcast, conflict free) with a division-free ray/segment test.  Replaces the shapely clipping of
+// one lane = one ray per fan.  Per CTA and tile of 1024 candidate edges (4 per obstacle rectangle + shared road-border
+// segments), ONCE:
+//   * transform into the ego frame, cull against the sensor disc, orient (cross(a, e) >= 0), compact into shared memory;
+//   * per edge: a distance key (squared ego distance of its closest point) and its angular interval relative to ray 0;
+//   * counting sort over 32 distance rings -> the staged edges in near-to-far order.
+// Per fan: the staged edges whose angular interval meets the fan's are appended IN ORDER to a shared list (five
+// compares per edge; round 2a recomputed three cross products per edge and fan).  Every warp walks that list (all
+// lanes read the same word: broadcast) with a division-free ray/segment test, keeps the farthest current hit of its
+// 32 rays, skips edges whose key lies beyond it and leaves the list at the first ring that lies wholly beyond it:
+// in a cluttered scene the near occluders end the walk after a few edges.  Results are those of the plain loop over
+// all edges (first hit = minimum; the skip margins are conservative).  Replaces the shapely clipping of
 // sensor_model.py:103-193 (one polygon difference per border vertex / obstacle).
 #include <math_constants.h>
 
@@ -16,7 +21,8 @@
 namespace fo {
 
 constexpr int kVisThreads = 256;
-constexpr int kVisTile = 1024;   // staged edges per tile: 1024 * (16 + 8 + 2) B = 26 KB
+constexpr int kVisTile = 1024;   // staged edges per tile: 1024 * (16 + 8 + 8 + 4 + 4) B = 40 KB
+constexpr int kVisBins = 32;     // distance rings of the near-to-far ordering
 constexpr int kVisFans = 16;     // fans one CTA owns at most (one ray per lane and fan)
 constexpr int kVisTrCap = 512;   // listed transparent obstacles per frame (more: fall back to scanning all flags)
 
@@ -24,22 +30,20 @@ struct VisEdge {
   float4 g;   // a.x, a.y, e.x, e.y   (segment a -> a + e, ego frame)
 };
 
-// conservative culls.  Disc: segment entirely outside the disc of radius R.  Sector: segment entirely outside the
-// angular sector spanned (counter-clockwise) by unit vectors d0 -> d1 with mid direction dm (width <= 180 deg)
-__device__ __forceinline__ bool edge_in_disc(float ax, float ay, float bx, float by, float R2) {
+// squared distance from the ego (origin) to the closest point of a segment: the sensor-disc cull and the distance key
+__device__ __forceinline__ float edge_dist2(float ax, float ay, float bx, float by) {
   float ex = bx - ax, ey = by - ay;
   float l2 = fmaf(ex, ex, ey * ey);
   float t = l2 > 0.0f ? fminf(fmaxf(-(ax * ex + ay * ey) / l2, 0.0f), 1.0f) : 0.0f;
   float px = fmaf(t, ex, ax), py = fmaf(t, ey, ay);
-  return fmaf(px, px, py * py) <= R2;
+  return fmaf(px, px, py * py);            // squared distance ego -> closest point of the segment
 }
-__device__ __forceinline__ bool edge_in_sector(float ax, float ay, float bx, float by, float2 d0, float2 d1, float2 dm) {
-  float ca = d0.x * ay - d0.y * ax, cb = d0.x * by - d0.y * bx;   // cross(d0, p): < 0 -> clockwise of the fan
-  if (ca < 0.0f && cb < 0.0f) return false;
-  ca = ax * d1.y - ay * d1.x; cb = bx * d1.y - by * d1.x;         // cross(p, d1): < 0 -> beyond the fan
-  if (ca < 0.0f && cb < 0.0f) return false;
-  if (ax * dm.x + ay * dm.y < 0.0f && bx * dm.x + by * dm.y < 0.0f) return false;   // behind the ego
-  return true;
+constexpr float TWO_PI = 6.28318530717958647692f;
+constexpr float kVisPad = 2e-4f;   // angular padding of the per-fan cull (float32 atan2f / sincosf noise is ~1e-6)
+
+// ring index (pre-shifted to its bit field) from which every edge lies beyond distance `wmax` with a 0.2 % margin
+__device__ __forceinline__ uint32_t vis_ring_end(float wmax, float bin_scale) {
+  return (uint32_t)min(kVisBins, (int)ceilf(fmaf(wmax * bin_scale, 1.002f, 1e-3f))) << 10;
 }
 
 __device__ __forceinline__ void ray_angle_params(const FoVisibilityArgs& k, float heading, float& a0, float& da) {
@@ -54,11 +58,18 @@ __device__ __forceinline__ void ray_angle_params(const FoVisibilityArgs& k, floa
   }
 }
 
-__global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisibilityArgs k, const int fans_per_cta) {
+// COUNT: the instrumented twin behind fo_visibility_stats (work counters, never timed)
+template <bool COUNT>
+__global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisibilityArgs k, const int fans_per_cta,
+                                                                    unsigned long long* __restrict__ counters) {
   __shared__ float4 sg[kVisTile];       // a.x, a.y, e.x, e.y of the staged (disc-culled, oriented) edges
   __shared__ float2 st[kVisTile];       // (cross(a, e), owner as int bits)
-  __shared__ uint16_t s_idx[kVisTile];  // staged edges that touch the current fan's sector
-  __shared__ int s_count, s_nfan[2];    // s_nfan alternates between fans: the reset of one never races the readers of the other
+  __shared__ float2 sphi[kVisTile];     // angular interval [lo, hi] of the edge relative to ray 0, lo in [0, 2 pi), padded
+  __shared__ uint32_t s_sorted[kVisTile];  // staged edges near to far: (distance key, 17 bits) | ring << 10 | staged index
+  __shared__ uint32_t s_list[kVisTile]; // the current fan's edges, same words, same order (during staging: unsorted words)
+  __shared__ int s_bcount[kVisBins], s_boff[kVisBins];
+  __shared__ int s_wcnt[2][kVisThreads / 32];
+  __shared__ int s_count;
   __shared__ int s_ntr;                 // transparent (bicycle) obstacles of this frame
   __shared__ uint16_t s_tr[kVisTrCap];
   const int f = blockIdx.y;
@@ -67,9 +78,12 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   float a0, da;
   ray_angle_params(k, heading, a0, da);
   const float R = k.sensor_radius, R2 = R * R;
+  const float bin_scale = (float)kVisBins / R;
   const int fans_total = (k.n_rays + kVisThreads - 1) / kVisThreads;
   const int fan0 = blockIdx.x * fans_per_cta;
   const int n_fans = min(fans_per_cta, fans_total - fan0);
+
+  unsigned long long n_test = 0, n_skip = 0;   // COUNT only
 
   // a ray's running first hit lives in its output slots between the tiles of a frame with more than kVisTile edges
   float* const range_f = k.range + (size_t)f * k.n_rays;
@@ -96,12 +110,13 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   for (int base = 0; base < n_cand; base += kVisTile) {
     __syncthreads();                       // previous tile fully cast
     if (threadIdx.x == 0) s_count = 0;
+    if (threadIdx.x < kVisBins) s_bcount[threadIdx.x] = 0;
     __syncthreads();
     // ---- stage ONCE per CTA: transform to the ego frame, cull against the sensor disc, orient, compact ----------
     for (int q0 = base; q0 < min(base + kVisTile, n_cand); q0 += kVisThreads) {
       const int q = q0 + threadIdx.x;
       bool keep = false;
-      float ax = 0, ay = 0, bx = 0, by = 0;
+      float ax = 0, ay = 0, bx = 0, by = 0, d2 = 0;
       int own = FO_HIT_NONE;
       if (q < min(base + kVisTile, n_cand)) {
         if (q < n_rect_edges) {
@@ -118,13 +133,15 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
             ax = cx + sx0 * hl * cs - sy0 * hw * sn; ay = cy + sx0 * hl * sn + sy0 * hw * cs;
             bx = cx + sx1 * hl * cs - sy1 * hw * sn; by = cy + sx1 * hl * sn + sy1 * hw * cs;
             own = o;
-            keep = edge_in_disc(ax, ay, bx, by, R2);
+            d2 = edge_dist2(ax, ay, bx, by);
+            keep = d2 <= R2;
           }
         } else {
           const float4 b = reinterpret_cast<const float4*>(k.boundary)[q - n_rect_edges];
           ax = b.x - ex0; ay = b.y - ey0; bx = b.z - ex0; by = b.w - ey0;
           own = FO_HIT_BOUNDARY;
-          keep = edge_in_disc(ax, ay, bx, by, R2);
+          d2 = edge_dist2(ax, ay, bx, by);
+          keep = d2 <= R2;
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -140,71 +157,125 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
         }                                                    // sign products and absolute values
         sg[w] = make_float4(ax, ay, exx, eyy);
         st[w] = make_float2(tn, __int_as_float(own));
+        // distance key: squared ego distance of the closest point, shrunk by 0.2 % and truncated to 8 mantissa bits
+        // (both conservative); ring = its distance bin
+        const int b = min(kVisBins - 1, (int)(sqrtf(d2) * bin_scale));
+        s_list[w] = (__float_as_uint(d2 * 0.998f) & 0xffff8000u) | ((uint32_t)b << 10) | (uint32_t)w;
+        atomicAdd(&s_bcount[b], 1);
+        // angular interval, counter-clockwise from a to a + e (cross(a, e) >= 0: at most 180 deg), relative to ray 0
+        float ph = atan2f(ay, ax) - a0;
+        ph -= TWO_PI * floorf(ph * (1.0f / TWO_PI));
+        const float sp = atan2f(tn, fmaf(ax, ax + exx, ay * (ay + eyy)));
+        float lo = ph - kVisPad, hi = ph + sp + kVisPad;
+        if (lo < 0.0f) { lo += TWO_PI; hi += TWO_PI; }
+        if (d2 < 1e-12f) { lo = 0.0f; hi = 3.0f * TWO_PI; }      // the ego stands on the edge: every fan lists it
+        sphi[w] = make_float2(lo, hi);
       }
     }
     __syncthreads();
     const int cnt = s_count;
+    if (COUNT && threadIdx.x == 0) atomicAdd(&counters[2], (unsigned long long)cnt);
+    // near-to-far order of the staged edges (ring granularity): the cast then meets the close occluders first and skips
+    // every edge that lies beyond the farthest current hit of its warp's 32 rays
+    if (threadIdx.x < 32) {
+      const int c0 = s_bcount[lane];
+      int inc = c0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      s_boff[lane] = inc - c0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += kVisThreads) {
+      const uint32_t w = s_list[j];
+      const int b = (w >> 10) & 31u;
+      s_sorted[s_boff[b] + (atomicSub(&s_bcount[b], 1) - 1)] = w;
+    }
 
-    // ---- per fan: angular cull of the staged edges into an index list, then cast --------------------------------
+    // ---- per fan: angular cull of the staged edges into an ordered list, then cast -------------------------------
 #pragma unroll 1
     for (int q = 0; q < n_fans; ++q) {
       const int r_lo = (fan0 + q) * kVisThreads, r_hi = min(r_lo + kVisThreads, k.n_rays) - 1;
       const int r = r_lo + threadIdx.x;
-      const float span = da * (float)(r_hi - r_lo);
-      const bool use_sector = span < 3.0f;             // fans wider than 180 deg are not culled by angle
-      int* const nfan = &s_nfan[q & 1];
-      if (threadIdx.x == 0) *nfan = 0;
-      __syncthreads();                                 // previous fan's list fully consumed (its counter is the other slot)
-      if (use_sector) {
-        float2 d0, d1, dm;
-        sincosf(a0 + da * (float)r_lo - 1e-4f, &d0.y, &d0.x);
-        sincosf(a0 + da * (float)r_hi + 1e-4f, &d1.y, &d1.x);
-        sincosf(a0 + da * 0.5f * (float)(r_lo + r_hi), &dm.y, &dm.x);
-        for (int j0 = 0; j0 < cnt; j0 += kVisThreads) {
-          const int j = j0 + threadIdx.x;
-          bool keep = false;
-          if (j < cnt) {
-            const float4 g = sg[j];
-            keep = edge_in_sector(g.x, g.y, g.x + g.z, g.y + g.w, d0, d1, dm);
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          int pos = 0;
-          if (lane == 0 && m) pos = atomicAdd(nfan, __popc(m));
-          pos = __shfl_sync(0xffffffffu, pos, 0);
-          if (keep) s_idx[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+      const float f_lo = da * (float)r_lo, f_hi = da * (float)r_hi;
+      __syncthreads();                                 // s_sorted complete / previous fan's list fully consumed
+      int nf = 0;
+      for (int j0 = 0, par = 0; j0 < cnt; j0 += kVisThreads, par ^= 1) {
+        const int p = j0 + threadIdx.x;
+        bool keep = false;
+        uint32_t w = 0;
+        if (p < cnt) {
+          w = s_sorted[p];
+          const float2 ph = sphi[w & 1023u];
+          keep = ((ph.x <= f_hi) & (ph.y >= f_lo)) | (ph.y - TWO_PI >= f_lo);
         }
-      } else {
-        for (int j = threadIdx.x; j < cnt; j += kVisThreads) s_idx[j] = (uint16_t)j;
-        if (threadIdx.x == 0) *nfan = cnt;
+        // ordered append (no atomics): the list keeps the near-to-far order of s_sorted
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcnt[par][threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int ww = 0; ww < kVisThreads / 32; ++ww) {
+          const int c = s_wcnt[par][ww];
+          total += c;
+          before += ww < (int)(threadIdx.x >> 5) ? c : 0;
+        }
+        if (keep) s_list[nf + before + __popc(m & ((1u << lane) - 1u))] = w;
+        nf += total;
       }
       __syncthreads();
-      const int nf = *nfan;
-      if (r < k.n_rays) {
+      if (COUNT && threadIdx.x == 0) atomicAdd(&counters[3], (unsigned long long)nf);
+      if (r_lo + (int)(threadIdx.x & ~31u) < k.n_rays) {            // warp-uniform: the warp owns at least one ray
+        const bool live = r < k.n_rays;
         float c, s;
         sincosf(a0 + da * (float)r, &s, &c);
-        float bq = R;
+        float bq = live ? R : 0.0f;
         int oq = FO_HIT_NONE;
-        if (base > 0) { bq = range_f[r]; oq = hit_f[r]; }
+        if (base > 0 && live) { bq = range_f[r]; oq = hit_f[r]; }
+        // farthest current hit of the warp's rays, squared: an edge whose closest point is not nearer cannot improve any
+        float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(bq)));
+        float wmax2 = wmax * wmax;
+        uint32_t ring_end = vis_ring_end(wmax, bin_scale);          // first ring that lies wholly beyond wmax
 #pragma unroll 4
         for (int j = 0; j < nf; ++j) {
-          const int e = s_idx[j];
+          const uint32_t w = s_list[j];
+          if (__uint_as_float(w & 0xffff8000u) >= wmax2) {
+            if ((w & 0x7c00u) >= ring_end) break;                   // ordered by ring: nothing nearer follows
+            if (COUNT) ++n_skip;
+            continue;
+          }
+          if (COUNT) ++n_test;
+          const int e = w & 1023u;
           const float4 g = sg[e];
           const float2 t = st[e];
           const float D = c * g.w - s * g.z;           // cross(d, e)
           const float un = g.x * s - g.y * c;          // cross(a, d)
           // t = tn / D >= 0 with tn >= 0, u = un / D in [0, 1], t < best   (division-free, strict improvement only)
           const bool okk = (D > 0.0f) & (un >= 0.0f) & (un <= D) & (t.x < bq * D);
-          if (okk) {
-            bq = t.x / D;
-            oq = __float_as_int(t.y);
+          if (__any_sync(0xffffffffu, okk)) {
+            if (okk) {
+              bq = t.x / D;
+              oq = __float_as_int(t.y);
+            }
+            wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(bq)));
+            wmax2 = wmax * wmax;
+            ring_end = vis_ring_end(wmax, bin_scale);
           }
         }
-        range_f[r] = bq;
-        hit_f[r] = oq;
+        if (live) {
+          range_f[r] = bq;
+          hit_f[r] = oq;
+        }
       }
     }
   }
   __syncthreads();
+  if (COUNT) {
+    atomicAdd(&counters[0], n_test);                 // ray x edge tests executed (per lane)
+    if (lane == 0) atomicAdd(&counters[1], n_skip);  // edges a warp skipped on the distance key
+  }
 
 #pragma unroll 1
   for (int q = 0; q < n_fans; ++q) {
@@ -272,7 +343,7 @@ __global__ void fo_rollout_cv_kernel(const FoRolloutCvArgs k) {
 
 }  // namespace fo
 
-extern "C" int fo_visibility_raycast(const FoVisibilityArgs* a, void* stream) {
+static int visibility_launch(const FoVisibilityArgs* a, unsigned long long* counters, void* stream) {
   if (!a) { fo::set_error("fo_visibility_raycast: NULL args"); return FO_ERR_INVALID_ARG; }
   if (a->n_frames < 0 || a->n_rays < 0 || a->n_obstacles < 0 || a->n_boundary < 0) {
     fo::set_error("fo_visibility_raycast: negative size");
@@ -298,10 +369,19 @@ extern "C" int fo_visibility_raycast(const FoVisibilityArgs* a, void* stream) {
   while (fpc > 1 && (long long)a->n_frames * ((fans_total + fpc - 1) / fpc) < 4LL * sms) fpc >>= 1;
   if (fpc > fans_total) fpc = fans_total;
   dim3 grid((fans_total + fpc - 1) / fpc, a->n_frames);
-  fo::fo_visibility_kernel<<<grid, fo::kVisThreads, 0, st>>>(*a, fpc);
+  if (counters) fo::fo_visibility_kernel<true><<<grid, fo::kVisThreads, 0, st>>>(*a, fpc, counters);
+  else fo::fo_visibility_kernel<false><<<grid, fo::kVisThreads, 0, st>>>(*a, fpc, nullptr);
   fo::count_launch();
   FO_CUDA_TRY(cudaGetLastError());
   return FO_OK;
+}
+
+extern "C" int fo_visibility_raycast(const FoVisibilityArgs* a, void* stream) { return visibility_launch(a, nullptr, stream); }
+
+extern "C" int fo_visibility_stats(const FoVisibilityArgs* a, uint64_t* counters_dev, void* stream) {
+  if (!counters_dev) { fo::set_error("fo_visibility_stats: NULL counters"); return FO_ERR_INVALID_ARG; }
+  FO_CUDA_TRY(cudaMemsetAsync(counters_dev, 0, FO_VIS_STATS_K * sizeof(uint64_t), (cudaStream_t)stream));
+  return visibility_launch(a, reinterpret_cast<unsigned long long*>(counters_dev), stream);
 }
 
 extern "C" int fo_rollout_cv(const FoRolloutCvArgs* a, void* stream) {

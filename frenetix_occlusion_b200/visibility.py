@@ -36,10 +36,11 @@ def _dev(t, dtype, device):
 
 
 def raycast_frames(ego, rect, rect_flags, boundary, sensor_radius: float, sensor_angle_deg: float, n_rays: int,
-                   device="cuda:0", out: Optional[VisibilityResult] = None) -> VisibilityResult:
+                   device="cuda:0", out: Optional[VisibilityResult] = None, stats=None) -> VisibilityResult:
     """``ego`` [F,3] (x, y, heading); ``rect`` [F,O,5] (cx, cy, yaw, half_len, half_wid); ``rect_flags``
     [F,O] uint8 (RECT_EXISTS | RECT_TRANSPARENT); ``boundary`` [B,4] opaque segments or None.
-    Asynchronous on the current stream."""
+    Asynchronous on the current stream.  ``stats``: optional int64 device tensor of 4 work counters; the call then
+    runs the instrumented kernel (``fo_visibility_stats``) and ADDS its counters to it (diagnostics, not timed paths)."""
     if not torch.cuda.is_available():
         raise RuntimeError("frenetix_occlusion_b200 needs a CUDA device (no CPU fallback)")
     device = torch.device(device)
@@ -72,7 +73,12 @@ def raycast_frames(ego, rect, rect_flags, boundary, sensor_radius: float, sensor
             b.rect_flags = flags_d[f0:].data_ptr() if O else None
             b.range, b.hit = out.range[f0:].data_ptr(), out.hit[f0:].data_ptr()
             b.visible = out.visible[f0:].data_ptr() if O else None
-            L.check(L.lib.fo_visibility_raycast(C.byref(b), stream), "fo_visibility_raycast")
+            if stats is None:
+                L.check(L.lib.fo_visibility_raycast(C.byref(b), stream), "fo_visibility_raycast")
+            else:
+                part = torch.zeros(4, dtype=torch.int64, device=device)
+                L.check(L.lib.fo_visibility_stats(C.byref(b), C.c_void_p(part.data_ptr()), stream), "fo_visibility_stats")
+                stats += part
     out._keepalive = (ego_d, rect_d, flags_d, bnd_d)
     if isinstance(ego, torch.Tensor):
         out.angles0, out.dangle = None, 0.0

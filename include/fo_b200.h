@@ -194,6 +194,14 @@ typedef struct FoVisibilityArgs {
 
 int fo_visibility_raycast(const FoVisibilityArgs *args, void *stream);
 
+/* Work counters of one fo_visibility_raycast pass (same arguments; the outputs are written as well): what survives
+ * the culls.  counters_dev[FO_VIS_STATS_K] (device, zeroed by the call) = { ray x edge tests executed, (warp, edge)
+ * pairs skipped because the edge lies beyond the farthest current hit of the warp's rays, edges staged after the
+ * sensor-disc cull (summed over CTAs), edges listed by the per-fan sector cull (summed over fans) }.
+ * bench.py uses them for the executed-work roofline of the stage. */
+#define FO_VIS_STATS_K 4
+int fo_visibility_stats(const FoVisibilityArgs *args, uint64_t *counters_dev, void *stream);
+
 /* ---- stage 1 -> spawn locator: exact visibility / occlusion / road membership of query points -----
  * Replaces the shapely predicates SpawnLocator evaluates against SensorModel's products
  * (spawn_locator.py:263-275, 298, 406-444, 521, 552): `within` / `intersects` of points, lines and discs

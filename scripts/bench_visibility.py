@@ -38,6 +38,10 @@ for _ in range(5):
     b.synchronize()
     ts.append(a.elapsed_time(b))
 ms = float(np.mean(ts))
+cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+raycast_frames(ego, rect, flags, boundary, 50.0, 360.0, R, out=res, stats=cnt)
+torch.cuda.synchronize()
+tested, skipped, staged, listed = cnt.cpu().tolist()
 n_edges = 4 * O + (400 if ring else 0)
 tests = F * R * n_edges
 # CPU baseline leg: the float64 port of the ray cast on a few frames (the only use of oracle/ here)
@@ -48,7 +52,8 @@ for f in range(4):
     VO.raycast(np.zeros(3), rect_h[f], np.ones(O, np.uint8), None if boundary is None else boundary.cpu().numpy(), 50.0, 360.0, R)
 cpu_s = (time.perf_counter() - t0) / 4
 print(json.dumps({"workload": "C-vis", "frames": F, "rays": R, "obstacles": O, "boundary_edges": 400 if ring else 0,
-                  "kernel_ms": ms, "frames_per_s": F / (ms * 1e-3), "ray_edge_tests_per_s": tests / (ms * 1e-3),
+                  "kernel_ms": ms, "per_frame": {"tests_executed": tested / F, "warp_edge_skips": skipped / F,
+                                                  "staged_edges": staged / F, "fan_list_entries": listed / F}, "frames_per_s": F / (ms * 1e-3), "ray_edge_tests_per_s": tests / (ms * 1e-3),
                   "algorithmic_bytes": F * (O * 21 + R * 8 + O), "hbm_gbs": F * (O * 21 + R * 8 + O) / (ms * 1e-3) / 1e9,
                   "visible_fraction": float(res.visible.float().mean()), "mean_range": float(res.range.mean()),
                   "cpu_port_frames_per_s_1core": 1.0 / cpu_s}))

@@ -190,6 +190,14 @@ def test_full_size_visibility_sweep_properties(cuda_device):
     # ray (crossing rectangles), either may be reported as the owner -- the staging order of a frame's edges is not fixed
     assert (torch.cat((a.hit, b.hit)) != whole.hit).float().mean().item() < 1e-5
     assert (torch.cat((a.visible, b.visible)) != whole.visible).float().mean().item() < 1e-5
+    # the instrumented twin (fo_visibility_stats) writes the same outputs, and its counters nest as the culls do
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    c = raycast_frames(ego, rect, flags, None, 50.0, 360.0, R, stats=cnt)
+    torch.cuda.synchronize()
+    assert torch.equal(c.range.view(torch.int32), whole.range.view(torch.int32))
+    tested, skipped, staged, listed = cnt.cpu().tolist()
+    assert 0 < staged <= F * 4 * O and staged <= listed <= staged * (R // 256)
+    assert tested + 32 * skipped <= listed * 256 and 0 < tested < F * R * 4 * O
     perm = torch.randperm(O, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     p = raycast_frames(ego, rect[:, perm].contiguous(), flags[:, perm].contiguous(), None, 50.0, 360.0, R)
     torch.cuda.synchronize()
