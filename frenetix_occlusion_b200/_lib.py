@@ -76,6 +76,44 @@ class FoPointQueryArgs(C.Structure):
                 ("flags", C.c_void_p), ("blocker", C.c_void_p), ("lanelets", C.c_void_p)]
 
 
+class FoRasterSpec(C.Structure):
+    _fields_ = [("cx", C.c_double), ("cy", C.c_double), ("cs", C.c_double), ("sn", C.c_double),
+                ("hx", C.c_double), ("hy", C.c_double), ("cell", C.c_double), ("org_x", C.c_double), ("org_y", C.c_double),
+                ("nx", C.c_int32), ("ny", C.c_int32)]
+
+
+class FoRegionPredicate(C.Structure):
+    _fields_ = [("lanelet_mask", C.c_uint64), ("want_flags", C.c_uint32), ("reject_flags", C.c_uint32),
+                ("disc_x", C.c_double), ("disc_y", C.c_double), ("disc_r", C.c_double)]
+
+
+class FoRasterResult(C.Structure):
+    _fields_ = [("sum_x", C.c_double), ("sum_y", C.c_double), ("count", C.c_int32), ("contains", C.c_int32),
+                ("n_outline", C.c_int32), ("n_components", C.c_int32)]
+
+
+class FoSpawnRegionArgs(C.Structure):
+    _fields_ = [("frame", FoPointQueryArgs), ("raster", FoRasterSpec), ("pred", FoRegionPredicate),
+                ("probe_x", C.c_double), ("probe_y", C.c_double),
+                ("label", C.c_void_p), ("size", C.c_void_p), ("best", C.c_void_p), ("mask_dilated", C.c_void_p),
+                ("result", C.c_void_p)]
+
+
+class FoSpawnRectArgs(C.Structure):
+    _fields_ = [("frame", FoPointQueryArgs), ("raster", FoRasterSpec), ("pred", FoRegionPredicate),
+                ("centre_from", C.c_void_p), ("region_mask", C.c_void_p),
+                ("region_ox", C.c_double), ("region_oy", C.c_double), ("region_cell", C.c_double),
+                ("region_n", C.c_int32), ("outline_cap", C.c_int32),
+                ("mask", C.c_void_p), ("outline", C.c_void_p), ("result", C.c_void_p)]
+
+
+class FoHitsOnRoadArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int32), ("n_obstacles", C.c_int32), ("n_polygons", C.c_int32),
+                ("range", C.c_void_p), ("hit", C.c_void_p), ("ego", C.c_void_p), ("poly_xy", C.c_void_p), ("poly_off", C.c_void_p),
+                ("ego_x", C.c_double), ("ego_y", C.c_double), ("angle0", C.c_double), ("dangle", C.c_double),
+                ("org_x", C.c_double), ("org_y", C.c_double), ("on_road", C.c_void_p)]
+
+
 class FoRolloutCvArgs(C.Structure):
     _fields_ = [("n_agents", C.c_int32), ("n_states", C.c_int32), ("t_stride", C.c_int32), ("dt", C.c_double),
                 ("var0", C.c_double), ("var_factor", C.c_double),
@@ -109,6 +147,9 @@ _PROTOS = {
     "fo_visibility_raycast": (C.c_int, [C.POINTER(FoVisibilityArgs), C.c_void_p]),
     "fo_visibility_stats": (C.c_int, [C.POINTER(FoVisibilityArgs), C.c_void_p, C.c_void_p]),
     "fo_visibility_points": (C.c_int, [C.POINTER(FoPointQueryArgs), C.c_void_p]),
+    "fo_visibility_hits_on_road": (C.c_int, [C.POINTER(FoHitsOnRoadArgs), C.c_void_p]),
+    "fo_spawn_region": (C.c_int, [C.POINTER(FoSpawnRegionArgs), C.c_void_p]),
+    "fo_spawn_rect": (C.c_int, [C.POINTER(FoSpawnRectArgs), C.c_void_p]),
     "fo_rollout_cv": (C.c_int, [C.POINTER(FoRolloutCvArgs), C.c_void_p]),
     "fo_rollout_path": (C.c_int, [C.POINTER(FoRolloutPathArgs), C.c_void_p]),
     "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),

@@ -72,32 +72,36 @@ class OAPAgent:
     # The kernels store float32: positions are rolled out RELATIVE to the agent's start (origin = initial position,
     # subtracted and added back in float64 on the host), so world coordinates of 1e3 .. 1e4 m keep sub-micrometre
     # resolution instead of the 6e-5 .. 1e-3 m of an absolute float32 coordinate.
+    @staticmethod
+    def _host_rollout(packed, origins, sample=None):
+        """ONE read-back of a packed [6, J, T] rollout (x, y, yaw, v, var_x, var_y); origins [J, 2] added in float64."""
+        h = packed.cpu().numpy().astype(np.float64)                    # .cpu() synchronises
+        org = np.asarray(origins, dtype=np.float64).reshape(-1, 2)
+        out = {"x": h[0] + org[:, :1], "y": h[1] + org[:, 1:], "yaw": h[2], "v": h[3], "var": h[4]}
+        if sample is not None:
+            out["sample"] = sample.cpu().numpy()
+        return out
+
     def _rollout_cv(self, pos, velocity, phi, var_factor):
         org = (float(pos[0]), float(pos[1]))
         ro = rollout_cv([pos[0]], [pos[1]], [velocity], [phi], self.dt, self.horizon, 0.1, var_factor, origin=org,
                         device=self.device)
-        out = {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}   # .cpu() synchronises
-        out["x"] += org[0]
-        out["y"] += org[1]
-        return out
+        return self._host_rollout(ro["packed"], [org])
 
     def _rollout_path(self, paths, pos, velocity, var_factor):
         J = len(paths)
         org = (float(pos[0]), float(pos[1]))
         ro = rollout_path(paths, [pos[0]] * J, [pos[1]] * J, [velocity] * J, self.dt, self.horizon, 3.0, 0.1, var_factor,
                           origin=org, device=self.device)
-        out = {k: ro[k].cpu().numpy().astype(np.float64) for k in ("x", "y", "yaw", "v", "var")}
-        out["x"] += org[0]
-        out["y"] += org[1]
-        out["sample"] = ro["sample"].cpu().numpy()
-        return out
+        return self._host_rollout(ro["packed"], [org] * J, ro["sample"])
 
     def _prediction_dict(self, ro, j, n):
         x, y = ro["x"][j, :n], ro["y"][j, :n]
         var = ro["var"][j, :n]
+        cov = np.zeros((len(var), 2, 2))
+        cov[:, 0, 0] = cov[:, 1, 1] = var
         return {"orientation_list": np.array(ro["yaw"][j, :n]), "v_list": np.array(ro["v"][j, :n]),
-                "pos_list": np.column_stack((x, y)), "shape": self._buffered_shape(),
-                "cov_list": np.array([[[v, 0.0], [0.0, v]] for v in var])}
+                "pos_list": np.column_stack((x, y)), "shape": self._buffered_shape(), "cov_list": cov}
 
     def add_to_commonroad_scenario(self, timestep=0):
         """agent.py:225-252: the agent becomes a dynamic obstacle whose trajectory starts at timestep + 1.  With
@@ -135,17 +139,23 @@ class OAPAgent:
 
 class OAPPedestrianAgent(OAPAgent):
     def __init__(self, pos, velocity, agent_type, agent_params, scenario, config, dt=0.1, horizon=3.0, ref_path=None,
-                 visualization=None, debug=False, mode="ref_path", orientation=None, device="cuda:0"):
+                 visualization=None, debug=False, mode="ref_path", orientation=None, device="cuda:0", defer=False):
         super().__init__(pos, velocity, agent_type, agent_params, scenario, config, dt, horizon, visualization, debug, device)
         self.ego_reference_path = ref_path
         self.reference_curve = None
         phi = self._initial_orientation(mode, orientation)
         self.initial_state = State(position=self.initial_position, orientation=phi, velocity=self.initial_velocity, time_step=0)
-        # constant-velocity rollout on the device (agent.py:487-503)
-        vf = config["prediction"]["variance_factor"]
-        ro = self._rollout_cv(pos, velocity, phi, vf)
-        n = int(horizon / dt) + 1
-        self._full_prediction = self._prediction_dict(ro, 0, n)
+        # constant-velocity rollout on the device (agent.py:487-503); ``defer``: the manager rolls out all agents of a
+        # planning cycle in one launch and calls ``_finish``
+        self._job = ("cv", float(pos[0]), float(pos[1]), float(velocity), float(phi))
+        if not defer:
+            self._finish(self._rollout_cv(pos, velocity, phi, config["prediction"]["variance_factor"]), 0)
+
+    n_jobs = 1
+
+    def _finish(self, ro, j0):
+        n = int(self.horizon / self.dt) + 1
+        self._full_prediction = self._prediction_dict(ro, j0, n)
         self.trajectory = self._full_prediction["pos_list"]
         self.predictions = self._create_cr_predictions(0)
 
@@ -175,27 +185,30 @@ class OAPPedestrianAgent(OAPAgent):
 
 class OAPVehicleAgent(OAPAgent):
     def __init__(self, pos, velocity, agent_type, agent_params, scenario, config, dt=0.1, horizon=3.0,
-                 visualization=None, debug=False, device="cuda:0"):
+                 visualization=None, debug=False, device="cuda:0", defer=False):
         super().__init__(pos, velocity, agent_type, agent_params, scenario, config, dt, horizon, visualization, debug, device)
         self.route_planner = FORoutePlanner(scenario, scenario.lanelet_network, visualization, debug)
         self.reference_paths = self.route_planner.calc_possible_reference_paths(pos)
         self.initial_state = State(position=self.initial_position, orientation=self.route_planner.lanelet_orientation,
                                    velocity=self.initial_velocity, time_step=0)
-        vf = config["prediction"]["variance_factor"]
-        J = len(self.reference_paths)
-        ro = self._rollout_path([self._path_window(p, pos, velocity, horizon) for p in self.reference_paths], pos, velocity, vf)
-        n = int(horizon / dt) + 1
+        self._windows = [self._path_window(p, pos, velocity, horizon) for p in self.reference_paths]
+        self.n_jobs = len(self._windows)
+        self._job = ("path", float(pos[0]), float(pos[1]), float(velocity))
+        if not defer:
+            self._finish(self._rollout_path(self._windows, pos, velocity, config["prediction"]["variance_factor"]), 0)
+
+    def _finish(self, ro, j0):
+        J = self.n_jobs
+        n = int(self.horizon / self.dt) + 1
         smp = ro["sample"]
-        valid = [j for j in range(J) if smp[j] >= 0]
-        self._all_predictions = [self._prediction_dict(ro, j, n) for j in valid]
+        valid = [j for j in range(J) if smp[j0 + j] >= 0]
+        self._all_predictions = [self._prediction_dict(ro, j0 + j, n) for j in valid]
         # the trajectory a REAL agent drives (agent.py:348-362 with handler=None): the route whose reference path goes
         # straightest, i.e. the smallest variance of the path heading
         self._full_prediction = None
         if valid:
-            def heading_var(path):
-                d = np.diff(np.asarray(path, dtype=np.float64), axis=0)
-                return float(np.var(np.unwrap(np.arctan2(d[:, 1], d[:, 0]))))
-            best = min(range(len(valid)), key=lambda q: heading_var(self.reference_paths[valid[q]]))
+            hv = self.route_planner.heading_variances
+            best = min(range(len(valid)), key=lambda q: hv[valid[q]])
             self._full_prediction = self._all_predictions[best]
         self.predictions = self._create_cr_predictions(0)
 
@@ -269,7 +282,7 @@ class FOAgentManager:
     _PARAMS = {"bicycle": ("Bicycle", 4, 11.5), "car": ("Car", 7.32, 11.5), "truck": ("Truck", 7.32, 7)}
 
     def add_agent(self, pos, velocity="default", agent_type="Car", add_to_scenario=False, timestep=0, horizon=3.0,
-                  mode="ref_path", orientation=None):
+                  mode="ref_path", orientation=None, _defer=False):
         """agent.py:48-157 (same defaults, same errors)."""
         if self.timestep != timestep:
             return
@@ -305,11 +318,14 @@ class FOAgentManager:
             agent = self.pedestrian_cls(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
                                        scenario=self.scenario, dt=self.dt, horizon=horizon, ref_path=self.reference_path,
                                        visualization=self.visualization, debug=self.debug, mode=mode,
-                                       orientation=orientation, config=self.config, device=self.device)
+                                       orientation=orientation, config=self.config, device=self.device, defer=_defer)
         else:
             agent = self.vehicle_cls(pos=pos, velocity=velocity, agent_type=agent_type, agent_params=agent_params,
                                     scenario=self.scenario, dt=self.dt, horizon=horizon, visualization=self.visualization,
-                                    debug=self.debug, config=self.config, device=self.device)
+                                    debug=self.debug, config=self.config, device=self.device, defer=_defer)
+        if _defer:
+            self.phantom_agents.append(agent)
+            return agent
         if add_to_scenario:
             self.real_agents.append(agent)
             agent.add_to_commonroad_scenario(timestep=timestep)
@@ -319,6 +335,42 @@ class FOAgentManager:
             self.phantom_agents.append(agent)
             self._add_prediction(agent)
         return agent
+
+    def add_agents(self, specs):
+        """Phantom agents of one planning cycle at once: the same agents, ids and predictions as one ``add_agent`` call
+        per entry (``specs``: dicts of its keyword arguments), but ONE ``fo_rollout_cv`` launch for all pedestrians, ONE
+        ``fo_rollout_path`` launch for all vehicle routes and one read-back each instead of a launch and a blocking
+        copy per agent."""
+        specs = [dict(s) for s in specs]
+        if any(s.get("add_to_scenario") for s in specs) or len({float(s.get("horizon", 3.0)) for s in specs}) > 1:
+            return [self.add_agent(**s) for s in specs]
+        agents = [self.add_agent(_defer=True, **s) for s in specs]
+        live = [a for a in agents if a is not None]
+        vf = self.config["prediction"]["variance_factor"]
+        peds = [a for a in live if a._job[0] == "cv"]
+        vehs = [a for a in live if a._job[0] == "path" and a.n_jobs > 0]
+        ro_p = ro_v = None
+        if peds:
+            j = np.array([a._job[1:] for a in peds])
+            ro_p = rollout_cv(j[:, 0], j[:, 1], j[:, 2], j[:, 3], self.dt, peds[0].horizon, 0.1, vf, origin=j[:, :2], device=self.device)
+        if vehs:
+            paths = [w for a in vehs for w in a._windows]
+            j = np.array([a._job[1:] for a in vehs for _ in range(a.n_jobs)])
+            ro_v = rollout_path(paths, j[:, 0], j[:, 1], j[:, 2], self.dt, vehs[0].horizon, 3.0, 0.1, vf, origin=j[:, :2],
+                                device=self.device)
+            host_v = OAPAgent._host_rollout(ro_v["packed"], j[:, :2], ro_v["sample"])
+        if peds:
+            host_p = OAPAgent._host_rollout(ro_p["packed"], np.array([a._job[1:3] for a in peds]))
+        jp = jv = 0
+        for a in live:                                  # finish in creation order: prediction ids keep their order
+            if a._job[0] == "cv":
+                a._finish(host_p, jp)
+                jp += 1
+            else:
+                a._finish(host_v if a.n_jobs else {"sample": np.zeros(0, np.int32)}, jv)
+                jv += a.n_jobs
+            self._add_prediction(a)
+        return agents
 
     def agent_by_prediction_id(self, prediction_id):
         if not self.phantom_agents:

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
   __shared__ uint32_t s_sorted[kVisTile];  // staged edges near to far: (distance key, 17 bits) | ring << 10 | staged index
   __shared__ uint32_t s_list[kVisTile]; // the current fan's edges, same words, same order (during staging: unsorted words)
   __shared__ int s_bcount[kVisBins], s_boff[kVisBins];
-  __shared__ int s_wcnt[2][kVisThreads / 32];
+  __shared__ __align__(16) int s_wcnt[2][kVisThreads / 32];
   __shared__ int s_count;
   __shared__ int s_ntr;                 // transparent (bicycle) obstacles of this frame
   __shared__ uint16_t s_tr[kVisTrCap];
@@ -215,13 +215,13 @@ __global__ void __launch_bounds__(kVisThreads) fo_visibility_kernel(const FoVisi
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wcnt[par][threadIdx.x >> 5] = __popc(m);
         __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int ww = 0; ww < kVisThreads / 32; ++ww) {
-          const int c = s_wcnt[par][ww];
-          total += c;
-          before += ww < (int)(threadIdx.x >> 5) ? c : 0;
-        }
+        static_assert(kVisThreads == 256, "eight warp counts = two int4");
+        const int4 c0 = *reinterpret_cast<const int4*>(&s_wcnt[par][0]), c1 = *reinterpret_cast<const int4*>(&s_wcnt[par][4]);
+        const int wi = threadIdx.x >> 5;
+        const int p1 = c0.x, p2 = p1 + c0.y, p3 = p2 + c0.z, p4 = p3 + c0.w, p5 = p4 + c1.x, p6 = p5 + c1.y, p7 = p6 + c1.z;
+        const int total = p7 + c1.w;
+        const int lo4 = wi & 2 ? (wi & 1 ? p3 : p2) : (wi & 1 ? p1 : 0), hi4 = wi & 2 ? (wi & 1 ? p7 : p6) : (wi & 1 ? p5 : p4);
+        const int before = wi & 4 ? hi4 : lo4;
         if (keep) s_list[nf + before + __popc(m & ((1u << lane) - 1u))] = w;
         nf += total;
       }

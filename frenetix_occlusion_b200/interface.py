@@ -140,13 +140,15 @@ class FOInterface:
                                                          ego_orientation=self.ego_orientation, obstacles=self.fo_obstacles)
         self.fo_obstacles.update_multipolygon()
         self.spawn_points = self.spawn_locator.find_spawn_points(self.ego_pos, self.ego_orientation, self.ego_pos_cl, ego_v)
-        for sp in self.spawn_points:
-            mode = "lane_center" if sp.source == "left turn" or sp.source == "right turn" else "ref_path"
-            self.agent_manager.add_agent(pos=sp.position, velocity="default", agent_type=sp.agent_type,
-                                         timestep=self.timestep, horizon=3.0, mode=mode, orientation=sp.orientation)
-            if self.debug:
+        # interface.py:187-198, all phantom agents of the cycle rolled out in one device pass
+        self.agent_manager.add_agents([
+            dict(pos=sp.position, velocity="default", agent_type=sp.agent_type, timestep=self.timestep, horizon=3.0,
+                 mode="lane_center" if sp.source == "left turn" or sp.source == "right turn" else "ref_path",
+                 orientation=sp.orientation) for sp in self.spawn_points])
+        if self.debug:
+            for sp, agent in zip(self.spawn_points, self.agent_manager.phantom_agents):
                 print("Phantom agent of type {} with id {} added to scenario at position {}"
-                      .format(sp.agent_type, self.agent_manager.phantom_agents[-1].agent_id, sp.position))
+                      .format(sp.agent_type, agent.agent_id, sp.position))
         self.agent_manager.update_real_agents(self.predictions)
         if self.visualization is not None and self.plot:
             self.visualization.draw_predictions(self.agent_manager.predictions, label=False)

@@ -17,8 +17,9 @@ def rollout_cv(x0, y0, v, phi, dt: float, horizon: float, var0: float = 0.1, var
     if not torch.cuda.is_available():
         raise RuntimeError("frenetix_occlusion_b200 needs a CUDA device (no CPU fallback)")
     device = torch.device(device)
-    x0 = np.atleast_1d(np.asarray(x0, dtype=np.float64)) - origin[0]
-    y0 = np.atleast_1d(np.asarray(y0, dtype=np.float64)) - origin[1]
+    org = np.asarray(origin, dtype=np.float64)          # (2,) shared, or [A, 2] one origin per agent
+    x0 = np.atleast_1d(np.asarray(x0, dtype=np.float64)) - org[..., 0]
+    y0 = np.atleast_1d(np.asarray(y0, dtype=np.float64)) - org[..., 1]
     v = np.atleast_1d(np.asarray(v, dtype=np.float64))
     phi = np.atleast_1d(np.asarray(phi, dtype=np.float64))
     A = len(x0)
@@ -33,7 +34,7 @@ def rollout_cv(x0, y0, v, phi, dt: float, horizon: float, var0: float = 0.1, var
         a.x, a.y, a.yaw, a.vel, a.var_x, a.var_y = [out[i].data_ptr() for i in range(6)]
         L.check(L.lib.fo_rollout_cv(C.byref(a), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
                 "fo_rollout_cv")
-    return {"x": out[0], "y": out[1], "yaw": out[2], "v": out[3], "var": out[4], "_keepalive": inp}
+    return {"x": out[0], "y": out[1], "yaw": out[2], "v": out[3], "var": out[4], "packed": out, "_keepalive": inp}
 
 
 def rollout_path(paths, x0, y0, v0, dt: float, horizon: float, t1: float = 3.0, var0: float = 0.1,
@@ -46,14 +47,15 @@ def rollout_path(paths, x0, y0, v0, dt: float, horizon: float, t1: float = 3.0, 
     device = torch.device(device)
     J = len(paths)
     T = int(horizon / dt) + 1
-    org = np.asarray(origin, dtype=np.float64)
-    pts = [np.asarray(p, dtype=np.float64).reshape(-1, 2) - org for p in paths]
+    org = np.asarray(origin, dtype=np.float64)          # (2,) shared, or [J, 2] one origin per job
+    orgs = np.broadcast_to(org, (J, 2))
+    pts = [np.asarray(p, dtype=np.float64).reshape(-1, 2) - orgs[j] for j, p in enumerate(paths)]
     if any(len(p) > 1024 for p in pts):
         raise ValueError("reference paths are limited to 1024 points (resample coarser)")
     off = np.concatenate(([0], np.cumsum([len(p) for p in pts]))).astype(np.int32)
     xy = np.concatenate(pts).astype(np.float32) if J else np.zeros((0, 2), np.float32)
-    st = np.stack([np.atleast_1d(np.asarray(x0, dtype=np.float64)) - org[0],
-                   np.atleast_1d(np.asarray(y0, dtype=np.float64)) - org[1],
+    st = np.stack([np.atleast_1d(np.asarray(x0, dtype=np.float64)) - orgs[:, 0],
+                   np.atleast_1d(np.asarray(y0, dtype=np.float64)) - orgs[:, 1],
                    np.atleast_1d(np.asarray(v0, dtype=np.float64))])
     with torch.cuda.device(device):
         d_xy, d_off, d_st = (torch.from_numpy(a).to(device) for a in (xy, off, st))
@@ -68,5 +70,5 @@ def rollout_path(paths, x0, y0, v0, dt: float, horizon: float, t1: float = 3.0, 
         a.sample = smp.data_ptr()
         L.check(L.lib.fo_rollout_path(C.byref(a), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
                 "fo_rollout_path")
-    return {"x": out[0], "y": out[1], "yaw": out[2], "v": out[3], "var": out[4], "sample": smp,
+    return {"x": out[0], "y": out[1], "yaw": out[2], "v": out[3], "var": out[4], "sample": smp, "packed": out,
             "_keepalive": (d_xy, d_off, d_st)}

@@ -70,6 +70,12 @@ def route_reference_path(lanelet_network, route):
     return chaikins_corner_cutting(resample_fixed_step(np.concatenate(parts), 2.0), 4)
 
 
+def path_heading_variance(path) -> float:
+    """Variance of the (unwrapped) segment headings of a polyline: how straight a route's reference path goes."""
+    d = np.diff(np.asarray(path, dtype=np.float64), axis=0)
+    return float(np.var(np.unwrap(np.arctan2(d[:, 1], d[:, 0]))))
+
+
 class FORoutePlanner:
     def __init__(self, scenario, lanelet_network, visualization=None, debug=False):
         self.cr_scenario = scenario
@@ -88,10 +94,19 @@ class FORoutePlanner:
         start = self.cr_scenario.lanelet_network.find_lanelet_by_id(ids[0])
         self.start_lanelet = start
         self.lanelet_orientation = lanelet_orientation_at_position(start, pos)
-        self.route_candidates = [r for r in self._find_all_routes(ids[0], max_depth=2) if r]
-        self.reference_paths = []
-        for route in self.route_candidates:
-            self.reference_paths.append(route_reference_path(self.lanelet_network, route))
+        # routes and their reference paths depend on the start lanelet only and the lanelet network is static: computed
+        # once per start lanelet and network (the reference re-plans them for every phantom agent of every cycle)
+        cache = self.lanelet_network.__dict__.setdefault("_fo_route_cache", {})
+        hit = cache.get(ids[0])
+        if hit is None:
+            routes = [r for r in self._find_all_routes(ids[0], max_depth=2) if r]
+            paths = [route_reference_path(self.lanelet_network, route) for route in routes]
+            for q in paths:
+                q.setflags(write=False)
+            hit = cache[ids[0]] = (routes, paths, [path_heading_variance(q) for q in paths])
+        self.route_candidates = [list(r) for r in hit[0]]
+        self.reference_paths = list(hit[1])
+        self.heading_variances = list(hit[2])
         return self.reference_paths
 
     def _find_all_routes(self, id_lanelet_start, max_depth=2):

@@ -145,15 +145,16 @@ class SpawnLocator:
                 print("vehicles are on lanelets with opposite direction" if opposite
                       else "obstacle is coming from other direction")
 
-            region = self._occluded_region_raster(dyn_obst, possible_ids, opposite)
+            dx, dy = hf.vector_from_angle(dyn_obst.current_orientation)
+            probe = np.array([dyn_obst.current_pos[0] + 4 * dx, dyn_obst.current_pos[1] + 4 * dy])
+            region = self._occluded_region_raster(dyn_obst, possible_ids, opposite, probe)
             if region is None or region["area"] < self.min_area_threshold:
                 continue
             center_pos = region["centroid"]
             centroid_lanelet = self.scenario.lanelet_network.find_lanelet_by_position([center_pos])[0]
             if not any(e in relevant_lanelets for e in centroid_lanelet):
                 continue
-            dx, dy = hf.vector_from_angle(dyn_obst.current_orientation)
-            if region["contains"](np.array([dyn_obst.current_pos[0] + 4 * dx, dyn_obst.current_pos[1] + 4 * dy])):
+            if region["contains_probe"]:
                 continue
 
             rectangles = self._find_matching_rectangle(center_pos, region, dyn_obst, possible_ids, opposite)
@@ -192,8 +193,36 @@ class SpawnLocator:
         inside &= (flags & L.PT_FOCUS_NEAR) == 0          # - current_polygon.buffer(1), spawn_locator.py:275
         return inside
 
-    def _occluded_region_raster(self, dyn_obst, possible_ids, opposite):
-        """Largest connected part of the relevant occluded area on a ``raster_cell`` grid (spawn_locator.py:270-287)."""
+    def _lanelet_mask(self, possible_ids):
+        """Bit mask of the lanelet polygons ``possible_ids`` for the device predicate; None when one of them lies beyond
+        the 64 polygons the kernel reports (then the host path below is used)."""
+        bits = 0
+        for lid in possible_ids:
+            idx = self._lanelet_index(lid)
+            if idx >= 64:
+                return None
+            bits |= 1 << idx
+        return bits
+
+    def _occluded_region_raster(self, dyn_obst, possible_ids, opposite, probe):
+        """Largest connected part of the relevant occluded area on a ``raster_cell`` grid (spawn_locator.py:270-287):
+        generated, classified, labelled and reduced on the device (``fo_spawn_region``)."""
+        c = self.raster_cell
+        half = self.buffer_around_vehicle_from_side
+        n = int(np.ceil(2 * half / c))
+        bits = self._lanelet_mask(possible_ids)
+        if bits is None:
+            return self._occluded_region_raster_host(dyn_obst, possible_ids, opposite, probe)
+        k = self.sensor_model._obstacle_index[dyn_obst.cr_obstacle.obstacle_id]
+        want = L.PT_FOCUS_SHADOW if opposite else L.PT_OCCLUDED
+        count, centroid, inside, _, handle = self.sensor_model._frame.spawn_region(
+            dyn_obst.current_pos, half, c, n, bits, want, L.PT_FOCUS_NEAR, half, probe, k, 1.0)
+        if count == 0:
+            return None
+        return {"area": float(count) * c * c, "centroid": centroid, "contains_probe": inside, "handle": handle}
+
+    def _occluded_region_raster_host(self, dyn_obst, possible_ids, opposite, probe):
+        """The same on host rasters (networks with more than 64 lanelet polygons)."""
         from scipy import ndimage
         c = self.raster_cell
         half = self.buffer_around_vehicle_from_side
@@ -210,18 +239,32 @@ class SpawnLocator:
         comp = lab == best
         pts = P.reshape(n, n, 2)[comp]
         origin = np.array([dyn_obst.current_pos[0] - half, dyn_obst.current_pos[1] - half])
-
-        def contains(q):
-            ij = np.floor((np.asarray(q, dtype=np.float64) - origin) / c).astype(int)
-            return bool(0 <= ij[0] < n and 0 <= ij[1] < n and comp[ij[0], ij[1]])
-
+        ij = np.floor((np.asarray(probe, dtype=np.float64) - origin) / c).astype(int)
+        inside_probe = bool(0 <= ij[0] < n and 0 <= ij[1] < n and comp[ij[0], ij[1]])
         return {"area": float(comp.sum()) * c * c, "centroid": pts.mean(0), "mask": comp, "origin": origin, "n": n,
-                "contains": contains}
+                "contains_probe": inside_probe}
 
     def _find_matching_rectangle(self, position, region, dyn_obst, possible_ids, opposite):
         """spawn_locator.py:695-726: clip a 5.5 x 2.5 m box (car) and a 2 x 1 m box (bicycle) with the allowed area
         and rate how rectangular the remainder is (Jaccard index against its minimum rotated rectangle)."""
         _, orientation = self._find_orientation_at_position(position)
+        if "handle" in region:       # both boxes in one device pass (``fo_spawn_rect``), one read-back
+            c = self.rect_cell
+            res = self.sensor_model._frame.spawn_rects(region["handle"], [(position, 5.5, 2.5, False), (position, 2.0, 1.0, True)],
+                                                       orientation, c)
+            out, centre = {}, np.asarray(position, dtype=np.float64)
+            for key, (count, centroid, outline) in zip(("Car", "Bicycle"), res):
+                area = float(count) * c * c
+                if count < 3:
+                    out[key] = {"area": area, "area_ratio": 0.0, "jaccard_similarity": 0.0, "centroid": centre}
+                else:
+                    _, w, h, ang = hf.min_area_rectangle(outline)
+                    grow = c * (abs(np.cos(ang - orientation)) + abs(np.sin(ang - orientation)))
+                    mbr_area = (w + grow) * (h + grow)
+                    ratio = min(area / mbr_area, 1.0) if mbr_area > 0 else 0.0
+                    out[key] = {"area": area, "area_ratio": ratio, "jaccard_similarity": ratio, "centroid": centroid}
+                    centre = centroid          # the bicycle box is centred on what is left of the car box
+            return out
         vehicle = self._clipped_rectangle_metrics(position, 5.5, 2.5, orientation, region, dyn_obst, possible_ids, opposite)
         bike_center = vehicle["centroid"] if vehicle["area"] > 0 else position
         bike = self._clipped_rectangle_metrics(bike_center, 2.0, 1.0, orientation, region, dyn_obst, possible_ids, opposite)
@@ -448,7 +491,7 @@ class SpawnLocator:
         if phantom_pos is None:      # the reference would keep walking until the coordinate system raises
             return
         others = self.fo_obstacles.visible_obstacle_multipolygon or []
-        if any(hf.point_ring_distance(phantom_pos[None], ring)[0] <= 0.5 for ring in others):
+        if hf.point_rings_min_distance(phantom_pos, others) <= 0.5:
             return
         _, ego_lanelet_orientation = self._find_orientation_at_position(self.ego_pos)
         _, phantom_lanelet_orientation = self._find_orientation_at_position(phantom_pos)

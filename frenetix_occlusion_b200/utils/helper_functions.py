@@ -65,6 +65,29 @@ def point_ring_distance(P, ring) -> np.ndarray:
     return np.where(point_in_convex_ring(P, ring), 0.0, d)
 
 
+def point_rings_min_distance(p, rings) -> float:
+    """min over convex rings of ``point_ring_distance(p, ring)`` for ONE point (inf without rings): all rings in one
+    vectorised pass when they have the same vertex count (obstacle rectangles)."""
+    if rings is None or len(rings) == 0:
+        return float("inf")
+    try:
+        R = np.asarray(rings, dtype=np.float64)
+    except ValueError:
+        R = None
+    if R is None or R.ndim != 3:
+        return float(min(point_ring_distance(np.asarray(p)[None], ring)[0] for ring in rings))
+    p = np.asarray(p, dtype=np.float64).reshape(2)
+    e = np.roll(R, -1, axis=1) - R
+    rel = p - R
+    l2 = np.maximum((e * e).sum(-1), 1e-18)
+    t = np.clip((rel * e).sum(-1) / l2, 0.0, 1.0)
+    q = R + t[..., None] * e
+    d = np.hypot(p[0] - q[..., 0], p[1] - q[..., 1]).min(1)
+    cr = e[..., 0] * rel[..., 1] - e[..., 1] * rel[..., 0]
+    inside = np.all(cr >= 0, 1) | np.all(cr <= 0, 1)
+    return float(np.where(inside, 0.0, d).min())
+
+
 def _segments_intersect(a, b, c, d) -> bool:
     def orient(p, q, r):
         return (q[0] - p[0]) * (r[1] - p[1]) - (q[1] - p[1]) * (r[0] - p[0])
@@ -124,12 +147,9 @@ def min_area_rectangle(points):
         return 0.0, 0.0, 0.0, 0.0
     e = np.roll(hull, -1, axis=0) - hull
     ang = np.unique(np.mod(np.arctan2(e[:, 1], e[:, 0]), np.pi / 2))
-    best = (np.inf, 0.0, 0.0, 0.0)
-    for a in ang:
-        c, s = np.cos(a), np.sin(a)
-        u = hull @ np.array([c, s])
-        v = hull @ np.array([-s, c])
-        w, h = u.max() - u.min(), v.max() - v.min()
-        if w * h < best[0]:
-            best = (w * h, w, h, a)
-    return best
+    c, s = np.cos(ang), np.sin(ang)
+    u = hull[:, :1] * c + hull[:, 1:] * s              # [H, K]: all caliper directions at once
+    v = hull[:, 1:] * c - hull[:, :1] * s
+    w, h = u.max(0) - u.min(0), v.max(0) - v.min(0)
+    k = int(np.argmin(w * h))                          # first minimum in angle order
+    return float(w[k] * h[k]), float(w[k]), float(h[k]), float(ang[k])

@@ -89,6 +89,25 @@ def raycast_frames(ego, rect, rect_flags, boundary, sensor_radius: float, sensor
 
 
 _PIN_CACHE = {}
+_SPAWN_WS = {}
+_SPAWN_MAX_BOXES, _SPAWN_OUTLINE_CAP, _SPAWN_RECT_CELLS = 4, 8192, 1 << 16
+
+
+def _spawn_workspace(dev, cells):
+    """Device / pinned scratch of the spawn-region calls, shared per device (every call ends with a synchronisation)."""
+    key = str(dev)
+    ws = _SPAWN_WS.get(key)
+    if ws is None or ws["cells"] < cells:
+        ws = {"cells": cells, "rect_cells": _SPAWN_RECT_CELLS,
+              "label": torch.empty(cells, dtype=torch.int32, device=dev), "size": torch.empty(cells, dtype=torch.int32, device=dev),
+              "best": torch.zeros(1, dtype=torch.int64, device=dev), "dilated": torch.empty(cells, dtype=torch.uint8, device=dev),
+              "rect_mask": torch.empty(_SPAWN_RECT_CELLS, dtype=torch.uint8, device=dev),
+              "result": torch.zeros(32 * (_SPAWN_MAX_BOXES + 1), dtype=torch.uint8, device=dev),
+              "outline": torch.empty((_SPAWN_MAX_BOXES, _SPAWN_OUTLINE_CAP, 2), dtype=torch.float64, device=dev),
+              "result_host": torch.zeros(32 * (_SPAWN_MAX_BOXES + 1), dtype=torch.uint8).pin_memory(),
+              "outline_host": torch.empty((_SPAWN_MAX_BOXES, _SPAWN_OUTLINE_CAP, 2), dtype=torch.float64).pin_memory()}
+        _SPAWN_WS[key] = ws
+    return ws
 _QUERY_CACHE = {}
 
 
@@ -186,6 +205,97 @@ class FrameGeometry:
             host = buf.cpu().numpy()          # one copy, synchronises
         return host[:4 * n_rays].view(np.float32), host[4 * n_rays:8 * n_rays].view(np.int32), \
             (host[8 * n_rays:8 * n_rays + O] if O else np.zeros(0, np.uint8))
+
+    # ---- spawn locator, behind-dynamic-obstacle finder on the device (fo_spawn_region / fo_spawn_rect) --------------
+    def _frame_args(self, focus_obstacle: int, focus_margin: float):
+        a = L.FoPointQueryArgs()
+        a.n_points, a.n_obstacles, a.n_boundary, a.n_polygons = 0, self.n_obstacles, self.n_boundary, self.n_polygons
+        a.ego = self.ego_d.data_ptr()
+        a.rect = self.rect_d.data_ptr() if self.n_obstacles else None
+        a.rect_flags = self.flags_d.data_ptr() if self.n_obstacles else None
+        a.boundary = self.bnd_d.data_ptr() if self.n_boundary else None
+        a.poly_xy = self.poly_xy_d.data_ptr() if self.n_polygons else None
+        a.poly_off = self.poly_off_d.data_ptr() if self.n_polygons else None
+        a.sensor_radius, a.sensor_angle_deg = self.sensor_radius, self.sensor_angle_deg
+        a.occluded_radius, a.focus_obstacle, a.focus_margin = self.occluded_radius, int(focus_obstacle), float(focus_margin)
+        return a
+
+    def _raster_spec(self, centre, cs, sn, hx, hy, cell, nx, ny):
+        r = L.FoRasterSpec()
+        r.cx, r.cy, r.cs, r.sn, r.hx, r.hy, r.cell = float(centre[0]), float(centre[1]), float(cs), float(sn), float(hx), float(hy), float(cell)
+        r.org_x, r.org_y, r.nx, r.ny = float(self.origin[0]), float(self.origin[1]), int(nx), int(ny)
+        return r
+
+    @staticmethod
+    def _predicate(lanelet_mask, want_flags, reject_flags, disc_centre, disc_r):
+        p = L.FoRegionPredicate()
+        p.lanelet_mask, p.want_flags, p.reject_flags = int(lanelet_mask), int(want_flags), int(reject_flags)
+        p.disc_x, p.disc_y, p.disc_r = float(disc_centre[0]), float(disc_centre[1]), float(disc_r)
+        return p
+
+    def spawn_region(self, centre, half, cell, n, lanelet_mask, want_flags, reject_flags, disc_r, probe,
+                     focus_obstacle, focus_margin):
+        """Largest 4-connected part of {cells of the n x n raster around ``centre`` that satisfy the predicate}:
+        (count, centroid, probe-inside, handle).  The handle keeps the dilated mask of that part on the device for
+        ``spawn_rects``.  One launch sequence, one 32-byte read-back."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            cells = n * n
+            ws = _spawn_workspace(dev, cells)
+            a = L.FoSpawnRegionArgs()
+            a.frame = self._frame_args(focus_obstacle, focus_margin)
+            a.raster = self._raster_spec(centre, 1.0, 0.0, half, half, cell, n, n)
+            a.pred = self._predicate(lanelet_mask, want_flags, reject_flags, centre, disc_r)
+            a.probe_x, a.probe_y = float(probe[0]), float(probe[1])
+            a.label, a.size, a.best = ws["label"].data_ptr(), ws["size"].data_ptr(), ws["best"].data_ptr()
+            a.mask_dilated, a.result = ws["dilated"].data_ptr(), ws["result"].data_ptr()
+            st = torch.cuda.current_stream(dev)
+            L.check(L.lib.fo_spawn_region(C.byref(a), C.c_void_p(st.cuda_stream)), "fo_spawn_region")
+            ws["result_host"][:32].copy_(ws["result"][:32], non_blocking=True)
+            st.synchronize()
+            r = L.FoRasterResult.from_buffer_copy(ws["result_host"][:32].numpy().tobytes())
+        handle = {"pred": a.pred, "frame": a.frame, "ox": float(centre[0]) - float(half), "oy": float(centre[1]) - float(half),
+                  "cell": float(cell), "n": int(n), "ws": ws}
+        centroid = np.array([r.sum_x / r.count, r.sum_y / r.count]) if r.count else None
+        return r.count, centroid, bool(r.contains), r.n_components, handle
+
+    def spawn_rects(self, handle, boxes, orientation, cell):
+        """Candidate boxes clipped with the selected part (``handle`` of ``spawn_region``).  ``boxes``: list of
+        (centre, length, width, chain) -- ``chain`` = centre the box on what is left of the previous one when that has
+        at least 3 cells.  Returns per box (count, centroid or None, outline points [K, 2]); one read-back for all."""
+        dev = self.device
+        cs, sn = np.cos(orientation), np.sin(orientation)
+        ws = handle["ws"]
+        out = []
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev)
+            for b, (centre, length, width, chain) in enumerate(boxes):
+                nx, ny = int(round(length / cell)), int(round(width / cell))
+                if nx * ny > ws["rect_cells"] or b >= _SPAWN_MAX_BOXES:
+                    raise ValueError("candidate box raster larger than the spawn workspace")
+                a = L.FoSpawnRectArgs()
+                a.frame, a.pred = handle["frame"], handle["pred"]
+                a.raster = self._raster_spec(centre, cs, sn, 0.5 * length, 0.5 * width, cell, nx, ny)
+                a.centre_from = ws["result"][32 * b:].data_ptr() if (chain and b > 0) else None
+                a.region_mask = ws["dilated"].data_ptr()
+                a.region_ox, a.region_oy, a.region_cell, a.region_n = handle["ox"], handle["oy"], handle["cell"], handle["n"]
+                a.outline_cap = _SPAWN_OUTLINE_CAP
+                a.mask = ws["rect_mask"].data_ptr()
+                a.outline = ws["outline"][b].data_ptr()
+                a.result = ws["result"][32 * (b + 1):].data_ptr()
+                L.check(L.lib.fo_spawn_rect(C.byref(a), C.c_void_p(st.cuda_stream)), "fo_spawn_rect")
+            nb = len(boxes)
+            ws["result_host"][:32 * (nb + 1)].copy_(ws["result"][:32 * (nb + 1)], non_blocking=True)
+            ws["outline_host"][:nb].copy_(ws["outline"][:nb], non_blocking=True)
+            st.synchronize()
+            raw = ws["result_host"].numpy()
+            for b in range(nb):
+                r = L.FoRasterResult.from_buffer_copy(raw[32 * (b + 1):32 * (b + 2)].tobytes())
+                if r.n_outline > _SPAWN_OUTLINE_CAP:
+                    raise RuntimeError("outline of a candidate box exceeds the spawn workspace")
+                centroid = np.array([r.sum_x / r.count, r.sum_y / r.count]) if r.count else None
+                out.append((r.count, centroid, ws["outline_host"][b, :r.n_outline].numpy().copy()))
+        return out
 
     def classify(self, points, focus_obstacle: int = -1, focus_margin: float = 0.0):
         """Classify world-frame points [M,2]: returns host arrays (flags uint32, blocker int32, lanelets uint64)."""

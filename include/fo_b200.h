@@ -246,6 +246,93 @@ typedef struct FoPointQueryArgs {
 
 int fo_visibility_points(const FoPointQueryArgs *args, void *stream);
 
+/* Which obstacles are seen ON THE ROAD: the reference intersects every obstacle polygon with the road-clipped visible
+ * area (sensor_model.py:59-76); here an obstacle counts when some ray of a finished fo_visibility_raycast pass ends on
+ * it at a point inside a lanelet polygon.  Ray end points: ego + (range - 1e-3f) (cos a, sin a), a = angle0 + dangle r
+ * in float64, shifted by the frame origin, rounded to float32 and tested like fo_visibility_points' FO_PT_ON_ROAD. */
+typedef struct FoHitsOnRoadArgs {
+  int32_t n_rays, n_obstacles, n_polygons;
+  const float *range;          /* dev [R] of one frame */
+  const int32_t *hit;          /* dev [R] */
+  const float *ego;            /* dev [3] frame ego (relative to the frame origin), as FoPointQueryArgs.ego */
+  const float *poly_xy;        /* dev [V, 2] lanelet polygon rings relative to the frame origin */
+  const int32_t *poly_off;     /* dev [n_polygons + 1] */
+  double ego_x, ego_y;         /* ego position, caller's world frame */
+  double angle0, dangle;       /* ray r points along angle0 + dangle * r */
+  double org_x, org_y;         /* frame origin */
+  uint8_t *on_road;            /* dev [O] out (zeroed by the call) */
+} FoHitsOnRoadArgs;
+
+int fo_visibility_hits_on_road(const FoHitsOnRoadArgs *args, void *stream);
+
+/* ---- spawn locator, behind-dynamic-obstacle finder on the device --------------------------------------
+ * Replaces the shapely chain of SpawnLocator._find_spawn_point_behind_dynamic_obstacle (spawn_locator.py:254-287:
+ * possible_polygon ∩ (obstacle shadow | occluded area) ∩ disc − obstacle.buffer(1), largest part of the result, its
+ * area / centroid / `contains`) and of _find_matching_rectangle (spawn_locator.py:695-726: clip a candidate box with
+ * that part, area and centroid of the remainder, outline for the minimum rotated rectangle) by rasters that are
+ * generated, classified (same predicate code as fo_visibility_points), labelled and reduced on the device; the host
+ * reads back one small result record per raster.
+ *
+ * A raster is a grid of cell centres  P(i, j) = C + gx (cs, sn) + gy (-sn, cs),  gx = (i + 0.5) cell - hx,
+ * gy = (j + 0.5) cell - hy, i < nx, j < ny, evaluated in float64 exactly as written (no contraction), then shifted by
+ * the frame origin and rounded to float32 for the classification.  Linear cell index = i * ny + j. */
+typedef struct FoRasterSpec {
+  double cx, cy;               /* C, caller's world frame */
+  double cs, sn;               /* direction of the first axis */
+  double hx, hy;               /* half extents */
+  double cell;
+  double org_x, org_y;         /* frame origin: FoPointQueryArgs geometry is given relative to it */
+  int32_t nx, ny;
+} FoRasterSpec;
+
+typedef struct FoRegionPredicate {
+  uint64_t lanelet_mask;       /* a cell must lie in one of these lanelet polygons (bits as FoPointQueryArgs.lanelets) */
+  uint32_t want_flags;         /* ... carry one of these FO_PT_* flags (FO_PT_FOCUS_SHADOW or FO_PT_OCCLUDED) */
+  uint32_t reject_flags;       /* ... and none of these (FO_PT_FOCUS_NEAR) */
+  double disc_x, disc_y, disc_r;   /* ... within disc_r of this point (world frame, float64 hypot) */
+} FoRegionPredicate;
+
+typedef struct FoRasterResult {
+  double sum_x, sum_y;         /* sums of the selected cell centres (world frame): centroid = sum / count */
+  int32_t count;               /* selected cells (area = count * cell^2) */
+  int32_t contains;            /* region: 1 = the probe point lies in a selected cell */
+  int32_t n_outline;           /* rect: selected cells with a missing 4-neighbour (may exceed the outline capacity) */
+  int32_t n_components;        /* region: connected parts found */
+} FoRasterResult;
+
+typedef struct FoSpawnRegionArgs {
+  FoPointQueryArgs frame;      /* geometry, sensor and focus_obstacle / focus_margin; points, flags, blocker, lanelets and
+                                  n_points are ignored */
+  FoRasterSpec raster;         /* nx * ny <= 2^30 */
+  FoRegionPredicate pred;
+  double probe_x, probe_y;     /* point of FoRasterResult.contains */
+  int32_t *label;              /* dev [nx * ny] workspace; on return the component label of every cell (-1 = outside) */
+  int32_t *size;               /* dev [nx * ny] workspace */
+  unsigned long long *best;    /* dev [1] workspace */
+  uint8_t *mask_dilated;       /* dev [nx * ny] out: largest 4-connected part (first in raster order on ties, as
+                                  scipy.ndimage.label + argmax), dilated by one cell (4-neighbourhood) */
+  FoRasterResult *result;      /* dev [1] out */
+} FoSpawnRegionArgs;
+
+int fo_spawn_region(const FoSpawnRegionArgs *args, void *stream);
+
+typedef struct FoSpawnRectArgs {
+  FoPointQueryArgs frame;
+  FoRasterSpec raster;
+  FoRegionPredicate pred;
+  const FoRasterResult *centre_from;  /* dev, optional: when its count >= 3 the raster centre C is its centroid (the
+                                         bicycle box is centred on what is left of the car box, spawn_locator.py:702-704) */
+  const uint8_t *region_mask;  /* dev [region_n * region_n] FoSpawnRegionArgs.mask_dilated of the selected part */
+  double region_ox, region_oy, region_cell;   /* lower-left corner and cell of that raster */
+  int32_t region_n;
+  int32_t outline_cap;
+  uint8_t *mask;               /* dev [nx * ny] workspace */
+  double *outline;             /* dev [outline_cap, 2] out: centres of the outline cells (any order) */
+  FoRasterResult *result;      /* dev [1] out */
+} FoSpawnRectArgs;
+
+int fo_spawn_rect(const FoSpawnRectArgs *args, void *stream);
+
 /* ---- stage 2: phantom-agent rollouts ---------------------------------------------------------------
  * Constant-velocity pedestrian prediction: OAPPedestrianAgent._create_ped_trajectory (agent.py:451-505)
  * + _create_cr_predictions (agent.py:520-536) + create_cov_matrix (agent.py:260-280), written straight

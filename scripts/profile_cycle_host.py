@@ -29,6 +29,14 @@ for ts in steps:                                       # warm-up pass (first-cal
     st = ego.state(ts)
     fo.evaluate_scenario({}, st["pos"], st["orientation"], st["pos_cl"], st["v"], ts, ego.cosy)
 torch.cuda.synchronize()
+plain = {ts: [] for ts in steps}
+for _ in range(reps):
+    for ts in steps:
+        st = ego.state(ts)
+        t0 = time.perf_counter()
+        fo.evaluate_scenario({}, st["pos"], st["orientation"], st["pos_cl"], st["v"], ts, ego.cosy)
+        plain[ts].append((time.perf_counter() - t0) * 1e3)
+print({ts: round(min(v), 3) for ts, v in plain.items()}, "ms (min over", reps, "repeats, no profiler)")
 times = {ts: [] for ts in steps}
 pr = cProfile.Profile()
 for _ in range(reps):
@@ -43,3 +51,6 @@ print({ts: round(min(v), 3) for ts, v in times.items()}, "ms (min over", reps, "
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
 print(s.getvalue()[:9000])
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+print(s.getvalue()[:6000])

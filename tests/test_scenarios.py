@@ -310,3 +310,53 @@ def test_device_and_host_bundles_agree(cuda_device):
     assert len(fo.agent_manager.predictions) == 3
     assert torch.equal(r_host.valid, r_dev.valid) and 0 < int(r_host.valid.sum()) < len(fan)
     assert torch.allclose(r_host.summary, r_dev.summary, rtol=1e-4, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_device_spawn_region_equals_host_rasters(cuda_device):
+    """fo_spawn_region / fo_spawn_rect (rasters generated, labelled and reduced on the device) against the same rasters
+    classified point by point and processed with numpy / scipy.ndimage on the host: identical cell counts and probe
+    answers, centroids to float64 summation order, identical outline point sets."""
+    import torch
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.interface import FOInterface
+    from frenetix_occlusion_b200.scenario import scenario_from_dict
+    from frenetix_occlusion_b200.spawn_locator import SpawnLocator
+    seen = []
+    dev_region = SpawnLocator._occluded_region_raster
+    dev_rect = SpawnLocator._find_matching_rectangle
+
+    def region_both(self, dyn_obst, possible_ids, opposite, probe):
+        d = dev_region(self, dyn_obst, possible_ids, opposite, probe)
+        h = self._occluded_region_raster_host(dyn_obst, possible_ids, opposite, probe)
+        assert (d is None) == (h is None)
+        if d is not None:
+            assert d["area"] == h["area"] and d["contains_probe"] == h["contains_probe"]
+            assert np.abs(d["centroid"] - h["centroid"]).max() < 1e-9
+            d["host"] = h
+        seen.append(("region", None if d is None else d["area"]))
+        return d
+
+    def rect_both(self, position, region, dyn_obst, possible_ids, opposite):
+        d = dev_rect(self, position, region, dyn_obst, possible_ids, opposite)
+        h = dev_rect(self, position, region["host"], dyn_obst, possible_ids, opposite)
+        for key in ("Car", "Bicycle"):
+            assert d[key]["area"] == h[key]["area"], key
+            assert np.abs(np.asarray(d[key]["centroid"]) - np.asarray(h[key]["centroid"])).max() < 1e-9
+            assert abs(d[key]["jaccard_similarity"] - h[key]["jaccard_similarity"]) < 1e-9
+        seen.append(("rect", d["Car"]["area"], d["Bicycle"]["area"]))
+        return d
+
+    SpawnLocator._occluded_region_raster, SpawnLocator._find_matching_rectangle = region_both, rect_both
+    try:
+        for name in ("scene_scenario1.json", "scene_scenario2.json"):
+            doc = _load(name)
+            random.seed(7)
+            sc = scenario_from_dict(doc["scene"])
+            ego = R.OpenLoopEgo(sc)
+            fo = FOInterface(sc, ego.reference_path, R.DEFAULT_VEHICLE, sc.dt, config_path=R.deployment_config(agents=doc["agents"]))
+            R.replay(fo, ego, doc["timesteps"], fan_kwargs=None)
+        torch.cuda.synchronize()
+    finally:
+        SpawnLocator._occluded_region_raster, SpawnLocator._find_matching_rectangle = dev_region, dev_rect
+    assert sum(1 for s in seen if s[0] == "region" and s[1]) >= 2 and any(s[0] == "rect" and s[1] > 0 for s in seen), seen
