@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
   float4* const egoA = reinterpret_cast<float4*>(inv + kDtInvBytes);             // [T] (x, y, cos theta, sin theta)
   float2* const egoB = reinterpret_cast<float2*>(egoA + T);                      // [T] (theta, v)
   float* const dist = reinterpret_cast<float*>(egoB + T);                        // [T] cumulative chord length (BE)
-  const BeView bev{egoA, egoB, dist, inv};
+  const auto soff = [&](const void* q) { return (uint32_t)(reinterpret_cast<const unsigned char*>(q) - smem_raw); };
+  const BeView bev{soff(egoA), soff(egoB), soff(dist), soff(inv)};
+  const BeConst bek = be_const(k);
 
   const uint32_t mm = MASK ? MASK : k.mmask;
   const bool do_cp = mm & FO_M_CP, do_dce = mm & FO_M_DCE, do_hr = mm & FO_M_HR, do_be = mm & FO_M_BE,
@@ -454,10 +456,8 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
           todo &= todo - 1;
           const int ns_s = __shfl_sync(kFull, P.n_states, src);
           const float hl_s = __shfl_sync(kFull, P.hl, src), hw_s = __shfl_sync(kFull, P.hw, src);
-          bool range_err = false;
-          unsigned probes = 0;
-          const float r = be_bisect(k, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane, range_err, probes);
-          if (range_err) flags |= FO_F_BE_RANGE;
+          const float r = be_bisect(bek, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane).x;
+          if (r != r) flags |= FO_F_BE_RANGE;            // NaN: the re-timed path overruns the planned one
           if (lane == src) { rcd = r; btn = __fdividef(r, k.a_max); }
         }
         acc_rcd = fmaxf(acc_rcd, rcd);     // fmaxf ignores NaN

@@ -179,11 +179,29 @@ __device__ __forceinline__ float half_derf(float a, float b) {
   return 0.5f * r;
 }
 
+// Single MUFU forms.  __fdividef / __expf wrap the same MUFU.RCP / MUFU.EX2 in range guards (denormal divisor, result
+// below 2^-126: 4 and 3 more instructions per call) that cannot fire for the arguments used here; inside the guards'
+// dead range the results are bit-identical.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // erfc(z), z >= 0, fractional error < 1.2e-7 in exact arithmetic (Chebyshev fit of Numerical Recipes' erfcc:
 // t = 1/(1 + z/2), erfc = t exp(-z^2 + P9(t))); about 4e-6 relative in float32 because of the exponent's
-// magnitude -- two orders below the 1e-4 parity tolerance.  18 instructions instead of erfcf's ~45.
+// magnitude -- two orders below the 1e-4 parity tolerance.  17 instructions instead of erfcf's ~45.
+// RAW_EXP: exp as one FMUL + MUFU.EX2 (flushes results below 2^-126 to zero).  The summary kernel's cut-off keeps one end
+// of every evaluated interval within 4.7, so a flushed far end (< 1e-38 against >= 3e-11) cannot change a bit of the
+// factor; the detail kernel (no cut-off, per-step values compared for their first index) keeps the guarded __expf.
+template <bool RAW_EXP>
 __device__ __forceinline__ float erfc_pos_fast(float z) {
-  const float t = __fdividef(1.0f, fmaf(0.5f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.5f, z, 1.0f));      // 1 + z/2 >= 1: same bits as __fdividef(1, .)
   float p = 0.17087277f;
   p = fmaf(p, t, -0.82215223f);
   p = fmaf(p, t, 1.48851587f);
@@ -194,7 +212,8 @@ __device__ __forceinline__ float erfc_pos_fast(float z) {
   p = fmaf(p, t, 0.37409196f);
   p = fmaf(p, t, 1.00002368f);
   p = fmaf(p, t, -1.26551223f);
-  return t * __expf(fmaf(-z, z, p));
+  const float a = fmaf(-z, z, p);
+  return t * (RAW_EXP ? ex2_approx(a * 1.4426950216293334961f) : __expf(a));
 }
 
 // Collision probability of one gated step (collision_probability.py:94-122): Gaussian mass of the 3 obstacle
@@ -209,22 +228,26 @@ __device__ __forceinline__ float cp_gauss_boxes(float mx, float my, float hx, fl
                                                 float L6, float W2) {
   constexpr float kFar = 4.7f;
   float prob = 0.0f;
+  float fm = 0.0f;                 // obstacle point: centre, front, back
 #pragma unroll 1
-  for (int mb = 0; mb < 9; ++mb) {
-    const int m = mb / 3, bb = mb - 3 * m;
-    const float fm = (m == 0) ? 0.0f : (m == 1 ? 1.0f : -1.0f);
-    const float fb = (bb == 0) ? 0.0f : (bb == 1 ? 1.0f : -1.0f);
-    const float uy = fmaf(fm, hy, my), cyb = fb * by;
-    const float ya = (cyb - W2 - uy) * s2.y, yb = (cyb + W2 - uy) * s2.y;     // ya < yb
-    if (CUT && (ya > kFar || yb < -kFar)) continue;
-    const float ux = fmaf(fm, hx, mx), cxb = fb * bx;
-    const float xa = (cxb - L6 - ux) * s2.x, xb = (cxb + L6 - ux) * s2.x;
-    if (CUT && (xa > kFar || xb < -kFar)) continue;
-    const float eya = erfc_pos_fast(fabsf(ya)), eyb = erfc_pos_fast(fabsf(yb));
-    const float py = ((ya > 0.0f) == (yb > 0.0f)) ? fabsf(eya - eyb) : (2.0f - eya - eyb);
-    const float exa = erfc_pos_fast(fabsf(xa)), exb = erfc_pos_fast(fabsf(xb));
-    const float px = ((xa > 0.0f) == (xb > 0.0f)) ? fabsf(exa - exb) : (2.0f - exa - exb);
-    prob = fmaf(0.25f * px, py, prob);
+  for (int m = 0; m < 3; ++m) {
+    const float uy = fmaf(fm, hy, my), ux = fmaf(fm, hx, mx);
+    float fb = 0.0f;               // ego box: middle, front, rear
+#pragma unroll 1
+    for (int bb = 0; bb < 3; ++bb) {
+      const float cyb = fb * by, cxb = fb * bx;
+      fb = (bb == 0) ? 1.0f : -1.0f;
+      const float ya = (cyb - W2 - uy) * s2.y, yb = (cyb + W2 - uy) * s2.y;     // ya < yb
+      if (CUT && (ya > kFar || yb < -kFar)) continue;
+      const float xa = (cxb - L6 - ux) * s2.x, xb = (cxb + L6 - ux) * s2.x;
+      if (CUT && (xa > kFar || xb < -kFar)) continue;
+      const float eya = erfc_pos_fast<CUT>(fabsf(ya)), eyb = erfc_pos_fast<CUT>(fabsf(yb));
+      const float py = ((ya > 0.0f) == (yb > 0.0f)) ? fabsf(eya - eyb) : (2.0f - eya - eyb);
+      const float exa = erfc_pos_fast<CUT>(fabsf(xa)), exb = erfc_pos_fast<CUT>(fabsf(xb));
+      const float px = ((xa > 0.0f) == (xb > 0.0f)) ? fabsf(exa - exb) : (2.0f - exa - exb);
+      prob = fmaf(0.25f * px, py, prob);
+    }
+    fm = (m == 0) ? 1.0f : -1.0f;
   }
   return prob * (1.0f / 3.0f);
 }
@@ -243,22 +266,38 @@ __device__ __forceinline__ float lr4s_coef(float ang, float side, float rear) {
 }
 
 // ---- BE (be.py:66-193) shared by the summary kernels: warp-cooperative bisection on a re-timed ego path -----
+// The helpers are out of line (one copy per kernel).  Their view of the staged ego trajectory is a set of BYTE OFFSETS
+// into the kernel's dynamic shared memory, and the few kernel arguments they need travel by value: pointers and a
+// `const MetricKArgs&` would reach a noinline function as generic addresses (LD.E plus a uniform-register pair per access
+// instead of LDS / a register).
 constexpr int kBeBuckets = 64;   // arc-length -> state-index lookup used by the interpolation
 struct BeView {
-  const float4* egoA;   // [T] (x, y, cos theta, sin theta)
-  const float2* egoB;   // [T] (theta, v)
-  float* dist;          // [T] cumulative chord length (be.py:99)
-  uint8_t* inv;         // [kBeBuckets + 1] last state index with dist <= b * dmax / kBeBuckets
+  uint32_t egoA;   // float4 [T] (x, y, cos theta, sin theta)
+  uint32_t egoB;   // float2 [T] (theta, v)
+  uint32_t dist;   // float [T] cumulative chord length (be.py:99)
+  uint32_t inv;    // uint8 [kBeBuckets + 1] last state index with dist <= b * dmax / kBeBuckets
 };
+struct BeConst {
+  const float4* s0;   // agent-major states of the table
+  int T, Tp;
+  float dt, wb, hEx, hEy;
+};
+__device__ __forceinline__ BeConst be_const(const MetricKArgs& k) {
+  return BeConst{k.tab.s0, k.T, k.Tp, k.dt, k.wb, k.hEx, k.hEy};
+}
 
-static __device__ __noinline__ void be_prepare(const BeView w, int T, int lane) {
+static __device__ __noinline__ void be_prepare(const BeView v, int T, int lane) {
+  extern __shared__ __align__(16) unsigned char fo_dyn_smem[];
+  const float4* const egoA = reinterpret_cast<const float4*>(fo_dyn_smem + v.egoA);
+  float* const dist = reinterpret_cast<float*>(fo_dyn_smem + v.dist);
+  uint8_t* const inv = fo_dyn_smem + v.inv;
   float carry = 0.0f;
 #pragma unroll 1
   for (int i0 = 0; i0 < T; i0 += 32) {
     const int i = i0 + lane;
     float seg = 0.0f;
     if (i >= 1 && i < T) {
-      float4 p = w.egoA[i], q = w.egoA[i - 1];
+      float4 p = egoA[i], q = egoA[i - 1];
       seg = sqrtf((p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y));
     }
     float sc = seg;
@@ -267,20 +306,20 @@ static __device__ __noinline__ void be_prepare(const BeView w, int T, int lane) 
       float t = __shfl_up_sync(kFull, sc, o);
       if (lane >= o) sc += t;
     }
-    if (i < T) w.dist[i] = carry + sc;
+    if (i < T) dist[i] = carry + sc;
     carry += __shfl_sync(kFull, sc, 31);
   }
   __syncwarp();
-  const float bw = w.dist[T - 1] / (float)kBeBuckets;
+  const float bw = dist[T - 1] / (float)kBeBuckets;
 #pragma unroll 1
   for (int b = lane; b <= kBeBuckets; b += 32) {
     const float q = (b == kBeBuckets) ? CUDART_INF_F : (float)b * bw;
     int lo_j = 0, hi_j = T - 1;
     while (lo_j < hi_j) {
       const int mid = (lo_j + hi_j + 1) >> 1;
-      if (w.dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
+      if (dist[mid] <= q) lo_j = mid; else hi_j = mid - 1;
     }
-    w.inv[b] = (uint8_t)lo_j;
+    inv[b] = (uint8_t)lo_j;
   }
   __syncwarp();
 }
@@ -293,26 +332,35 @@ __device__ __forceinline__ float be_arclen(float dt, float v0, float v1, float s
   return (i == 0) ? 0.0f : dt * (v0 + fmaf(m, v1, -0.5f * step * m * (m - 1.0f)));
 }
 
-static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeView w, int a, int n_states, float hl, float hw,
-                                        float lo0, int lane, bool& range_err, unsigned& probes) {
+// Returns (required constant deceleration, number of probes as int bits); the deceleration is NaN when the re-timed
+// path overruns the planned one (the reference raises, be.py:117-124).
+static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v, int a, int n_states, float hl, float hw,
+                                                float lo0, int lane) {
+  extern __shared__ __align__(16) unsigned char fo_dyn_smem[];
+  const float4* const egoA = reinterpret_cast<const float4*>(fo_dyn_smem + v.egoA);
+  const float2* const egoB = reinterpret_cast<const float2*>(fo_dyn_smem + v.egoB);
+  const float* const dist = reinterpret_cast<const float*>(fo_dyn_smem + v.dist);
+  const uint8_t* const inv_tab = fo_dyn_smem + v.inv;
   const int T = k.T;
   const int nA = min(T, n_states);
-  const float v0 = w.egoB[0].y, v1 = w.egoB[T > 1 ? 1 : 0].y;
-  const float dmax = w.dist[T - 1];
+  const float v0 = egoB[0].y, v1 = egoB[T > 1 ? 1 : 0].y;
+  const float dmax = dist[T - 1];
   const float inv_w = dmax > 0.0f ? (float)kBeBuckets / dmax : 0.0f;
   // the agent's states do not depend on the probe: the first two 32-step chunks stay in registers for the whole
   // bisection (covers T <= 64, i.e. every horizon the reference uses), later chunks are re-read per probe
-  const float4* sa = k.tab.s0 + (size_t)a * k.Tp;
+  const float4* sa = k.s0 + (size_t)a * k.Tp;
   const float4 pre0 = (lane < nA) ? __ldg(sa + lane) : make_float4(0, 0, 1, 0);
   const float4 pre1 = (32 + lane < nA) ? __ldg(sa + 32 + lane) : make_float4(0, 0, 1, 0);
   float lo = lo0, hi = 5.0f, cur = 0.0f;
+  int probes = 0;
 #pragma unroll 1
   for (int it = 0; it < 10; ++it) {
     cur = 0.5f * (lo + hi);
     ++probes;
     const float step = cur * k.dt;
-    const float mpos = (step > 0.0f) ? fmaxf(floorf(__fdividef(v1, step)) + 1.0f, 0.0f) : 1.0e9f;
-    if (be_arclen(k.dt, v0, v1, step, mpos, T - 1) > dmax) { range_err = true; return CUDART_NAN_F; }
+    // step in [4e-4, 0.5]: v1 * rcp == __fdividef(v1, step) bit for bit
+    const float mpos = (step > 0.0f) ? fmaxf(floorf(v1 * rcp_approx(step)) + 1.0f, 0.0f) : 1.0e9f;
+    if (be_arclen(k.dt, v0, v1, step, mpos, T - 1) > dmax) return make_float2(CUDART_NAN_F, __int_as_float(probes));
     bool any_hit = false;
 #pragma unroll 1
     for (int i0 = 0; i0 < nA && !any_hit; i0 += 32) {
@@ -322,19 +370,19 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
         const float q = be_arclen(k.dt, v0, v1, step, mpos, i);
         // numpy.interp: j = last index with dist[j] <= q; start from the bucket's first candidate, fix a float32
         // off-by-one of the bucket index downwards, then walk up
-        int j = w.inv[min(__float2int_rd(q * inv_w), kBeBuckets - 1)];
-        while (j > 0 && w.dist[j] > q) --j;
-        while (j < T - 1 && w.dist[j + 1] <= q) ++j;
-        const float dj = w.dist[j];
-        const float4 A0 = w.egoA[j];
-        float xn = A0.x, yn = A0.y, tn = w.egoB[j].x;
+        int j = inv_tab[min(__float2int_rd(q * inv_w), kBeBuckets - 1)];
+        while (j > 0 && dist[j] > q) --j;
+        while (j < T - 1 && dist[j + 1] <= q) ++j;
+        const float dj = dist[j];
+        const float4 A0 = egoA[j];
+        float xn = A0.x, yn = A0.y, tn = egoB[j].x;
         if (j != T - 1 && dj != q) {
-          const float4 A1 = w.egoA[j + 1];
+          const float4 A1 = egoA[j + 1];
           const float wq = q - dj;
-          const float inv = 1.0f / (w.dist[j + 1] - dj);
+          const float inv = 1.0f / (dist[j + 1] - dj);
           xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
           yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
-          tn = fmaf((w.egoB[j + 1].x - tn) * inv, wq, tn);
+          tn = fmaf((egoB[j + 1].x - tn) * inv, wq, tn);
         }
         float sn, cn;
         __sincosf(tn, &sn, &cn);
@@ -350,7 +398,7 @@ static __device__ __noinline__ float be_bisect(const MetricKArgs& k, const BeVie
     if (nA > 0 && !any_hit) hi = cur; else lo = cur;   // be.py:74-77 (an agent that never exists counts as a hit)
     if (hi - lo < 0.1f) break;                         // be.py:79
   }
-  return cur;
+  return make_float2(cur, __int_as_float(probes));
 }
 
 struct EgoState {

@@ -122,7 +122,7 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 }
 __device__ __forceinline__ float warp_max_signed(float v) { return ord2f(__reduce_max_sync(kFull, f2ord(v))); }
 
-__device__ __forceinline__ float sw_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+__device__ __forceinline__ float sw_sigmoid(float z) { return rcp_approx(1.0f + __expf(-z)); }   // 1 + exp >= 1: same bits as __fdividef(1, .)
 
 // impact-angle class coefficients of both parties (one copy in the kernel: atan2f is ~150 instructions and the harm
 // logits are needed at five inlined sites; the kernel is instruction-cache-bound, not call-bound)
@@ -193,7 +193,9 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const float rE = sqrtf(k.hEx * k.hEx + k.hEy * k.hEy);   // ego circumradius
   const float cmax = fmaxf(0.0f, fmaxf(k.hc.rs_side, k.hc.rs_rear));
   const int Ap = k.tab.Ap;
-  const BeView bev{w.egoA, w.egoB, w.dist, w.inv};
+  const auto soff = [&](const void* q) { return (uint32_t)(reinterpret_cast<const unsigned char*>(q) - smem_raw); };
+  const BeView bev{soff(w.egoA), soff(w.egoB), soff(w.dist), soff(w.inv)};
+  const BeConst bek = be_const(k);
   // lane -> (agent within the lane group, time slice); every (warp, slice) owns a contiguous range of steps
   const int lg = shape.lg_agents;
   const int group = 1 << lg;                      // agents per warp pass
@@ -608,14 +610,12 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           for (int q = wib; q < n_be; q += W) {        // bisections dealt round-robin to the warps
             const int a = a0 + (int)w.be_list[q];
             const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
-            bool range_err = false;
-            unsigned probes = 0;
-            const float rcd = be_bisect(k, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane,
-                                        range_err, probes);
-            if (range_err) flags |= FO_F_BE_RANGE;
+            const float2 be = be_bisect(bek, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane);
+            const float rcd = be.x;
+            if (rcd != rcd) flags |= FO_F_BE_RANGE;      // NaN: the re-timed path overruns the planned one
             rcd_all = fmaxf(rcd_all, rcd);
             btn_all = fmaxf(btn_all, rcd / k.a_max);
-            if (STATS && lane == 0) { st_be += 1; st_probe += probes; }
+            if (STATS && lane == 0) { st_be += 1; st_probe += (unsigned)__float_as_int(be.y); }
           }
         }
         __syncthreads();                               // list consumed before the next tile refills it
