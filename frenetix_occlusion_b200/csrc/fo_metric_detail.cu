@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
   float2* const egoB = reinterpret_cast<float2*>(egoA + T);                      // [T] (theta, v)
   float* const dist = reinterpret_cast<float*>(egoB + T);                        // [T] cumulative chord length (BE)
   const auto soff = [&](const void* q) { return (uint32_t)(reinterpret_cast<const unsigned char*>(q) - smem_raw); };
-  const BeView bev{soff(egoA), soff(egoB), soff(dist), soff(inv)};
+  const BeView bev{soff(egoA), soff(egoB), soff(dist), soff(inv), 0u};
   const BeConst bek = be_const(k);
 
   const uint32_t mm = MASK ? MASK : k.mmask;
@@ -450,13 +450,13 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
       float rcd = 0.0f, btn = 0.0f;
       if (do_be && do_ttc) {
         unsigned todo = __ballot_sync(kFull, collides && t_col > 0);
-        if (todo && !be_ready) { be_prepare(bev, T, lane); be_ready = true; }    // arc length + bucket table, be.py:99
+        if (todo && !be_ready) { be_prepare<false>(bev, T, lane); be_ready = true; }    // arc length + bucket table, be.py:99
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
           const int ns_s = __shfl_sync(kFull, P.n_states, src);
           const float hl_s = __shfl_sync(kFull, P.hl, src), hw_s = __shfl_sync(kFull, P.hw, src);
-          const float r = be_bisect(bek, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane).x;
+          const float r = be_bisect<false>(bek, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane).x;
           if (r != r) flags |= FO_F_BE_RANGE;            // NaN: the re-timed path overruns the planned one
           if (lane == src) { rcd = r; btn = __fdividef(r, k.a_max); }
         }

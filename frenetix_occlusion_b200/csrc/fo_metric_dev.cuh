@@ -276,6 +276,8 @@ struct BeView {
   uint32_t egoB;   // float2 [T] (theta, v)
   uint32_t dist;   // float [T] cumulative chord length (be.py:99)
   uint32_t inv;    // uint8 [kBeBuckets + 1] last state index with dist <= b * dmax / kBeBuckets
+  uint32_t seg;    // float4 [T] (SEG variants only): per segment j -> j + 1 the slopes ((x1-x0) inv, (y1-y0) inv, (th1-th0) inv, 0),
+                   // inv = 1 / (dist[j+1] - dist[j]) -- the products be_bisect would form per lane and probe, formed once
 };
 struct BeConst {
   const float4* s0;   // agent-major states of the table
@@ -286,9 +288,12 @@ __device__ __forceinline__ BeConst be_const(const MetricKArgs& k) {
   return BeConst{k.tab.s0, k.T, k.Tp, k.dt, k.wb, k.hEx, k.hEy};
 }
 
+template <bool SEG>
 static __device__ __noinline__ void be_prepare(const BeView v, int T, int lane) {
   extern __shared__ __align__(16) unsigned char fo_dyn_smem[];
   const float4* const egoA = reinterpret_cast<const float4*>(fo_dyn_smem + v.egoA);
+  const float2* const egoB = reinterpret_cast<const float2*>(fo_dyn_smem + v.egoB);
+  float4* const seg = reinterpret_cast<float4*>(fo_dyn_smem + v.seg);
   float* const dist = reinterpret_cast<float*>(fo_dyn_smem + v.dist);
   uint8_t* const inv = fo_dyn_smem + v.inv;
   float carry = 0.0f;
@@ -310,6 +315,14 @@ static __device__ __noinline__ void be_prepare(const BeView v, int T, int lane) 
     carry += __shfl_sync(kFull, sc, 31);
   }
   __syncwarp();
+  if (SEG) {
+#pragma unroll 1
+    for (int j = lane; j < T - 1; j += 32) {
+      const float4 A0 = egoA[j], A1 = egoA[j + 1];
+      const float inv = 1.0f / (dist[j + 1] - dist[j]);     // a zero-length segment is never selected by the lookup
+      seg[j] = make_float4((A1.x - A0.x) * inv, (A1.y - A0.y) * inv, (egoB[j + 1].x - egoB[j].x) * inv, 0.0f);
+    }
+  }
   const float bw = dist[T - 1] / (float)kBeBuckets;
 #pragma unroll 1
   for (int b = lane; b <= kBeBuckets; b += 32) {
@@ -334,6 +347,7 @@ __device__ __forceinline__ float be_arclen(float dt, float v0, float v1, float s
 
 // Returns (required constant deceleration, number of probes as int bits); the deceleration is NaN when the re-timed
 // path overruns the planned one (the reference raises, be.py:117-124).
+template <bool SEG>
 static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v, int a, int n_states, float hl, float hw,
                                                 float lo0, int lane) {
   extern __shared__ __align__(16) unsigned char fo_dyn_smem[];
@@ -341,6 +355,7 @@ static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v,
   const float2* const egoB = reinterpret_cast<const float2*>(fo_dyn_smem + v.egoB);
   const float* const dist = reinterpret_cast<const float*>(fo_dyn_smem + v.dist);
   const uint8_t* const inv_tab = fo_dyn_smem + v.inv;
+  const float4* const seg = reinterpret_cast<const float4*>(fo_dyn_smem + v.seg);
   const int T = k.T;
   const int nA = min(T, n_states);
   const float v0 = egoB[0].y, v1 = egoB[T > 1 ? 1 : 0].y;
@@ -368,21 +383,35 @@ static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v,
       bool hit = false;
       if (i < nA) {
         const float q = be_arclen(k.dt, v0, v1, step, mpos, i);
-        // numpy.interp: j = last index with dist[j] <= q; start from the bucket's first candidate, fix a float32
-        // off-by-one of the bucket index downwards, then walk up
-        int j = inv_tab[min(__float2int_rd(q * inv_w), kBeBuckets - 1)];
-        while (j > 0 && dist[j] > q) --j;
+        // numpy.interp: j = last index with dist[j] <= q.  The bucket of q brackets it: j0 = inv[b] (stepped one bucket
+        // down when float32 rounding of the bucket index put it too high), j1 = inv[b + 1]; a bisection of [j0, j1] --
+        // most buckets hold at most one state -- and a final upward check for a q that rounded across the bucket's end
+        int b = min(__float2int_rd(q * inv_w), kBeBuckets - 1);
+        int j = inv_tab[b];
+        if (dist[j] > q) { b = max(b - 1, 0); j = inv_tab[b]; }
+        int jh = inv_tab[b + 1];
+        while (j < jh) {
+          const int mid = (j + jh + 1) >> 1;
+          if (dist[mid] <= q) j = mid; else jh = mid - 1;
+        }
         while (j < T - 1 && dist[j + 1] <= q) ++j;
         const float dj = dist[j];
         const float4 A0 = egoA[j];
         float xn = A0.x, yn = A0.y, tn = egoB[j].x;
         if (j != T - 1 && dj != q) {
-          const float4 A1 = egoA[j + 1];
           const float wq = q - dj;
-          const float inv = 1.0f / (dist[j + 1] - dj);
-          xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
-          yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
-          tn = fmaf((egoB[j + 1].x - tn) * inv, wq, tn);
+          if (SEG) {
+            const float4 sl = seg[j];
+            xn = fmaf(sl.x, wq, A0.x);
+            yn = fmaf(sl.y, wq, A0.y);
+            tn = fmaf(sl.z, wq, tn);
+          } else {
+            const float4 A1 = egoA[j + 1];
+            const float inv = 1.0f / (dist[j + 1] - dj);
+            xn = fmaf((A1.x - A0.x) * inv, wq, A0.x);
+            yn = fmaf((A1.y - A0.y) * inv, wq, A0.y);
+            tn = fmaf((egoB[j + 1].x - tn) * inv, wq, tn);
+          }
         }
         float sn, cn;
         __sincosf(tn, &sn, &cn);

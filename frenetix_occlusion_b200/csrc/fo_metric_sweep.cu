@@ -41,7 +41,10 @@
 namespace fo {
 
 constexpr int kSwMaxWarps = 8;
-constexpr int kSwTile = 256;      // agents per tile; bounds the per-team pair arrays
+#ifndef FO_SW_TILE
+#define FO_SW_TILE 128
+#endif
+constexpr int kSwTile = FO_SW_TILE;   // agents per tile (<= 256: 8-bit agent-in-tile field of the window items); bounds the per-team pair arrays
 constexpr int kSwQueue = 64;
 #ifndef FO_SW_MINB
 #define FO_SW_MINB 4
@@ -53,16 +56,18 @@ constexpr int kSwUnroll = FO_SW_UNROLL;
 constexpr int kSwWinQueue = 64;   // <= 31 left over + 32 from one filter step
 constexpr int kSwInvBytes = (kBeBuckets + 1 + 15) & ~15;   // arc-length bucket table, padded so that what follows stays 16-byte aligned
 
-__host__ __device__ inline size_t sweep_smem_bytes(int T, int W) {
+// The one-warp shape (uni) has no pooled leftovers; the rounding-tie queue exists only in the TIES variants.  At T = 51
+// the throughput shape needs 5.6 kB: 32 one-warp CTAs per SM (the register file's limit) fit in shared memory.
+__host__ __device__ inline size_t sweep_smem_bytes(int T, int W, bool uni, bool ties) {
   const size_t nW = (size_t)agent_windows(T);
   size_t b = (size_t)kSwTile * (8 + 4 + 2)       // pairkey, colfirst, BE pair list
              + 8 * 4 + kSwInvBytes               // scalars, arc-length bucket table
              + (size_t)kSwWinQueue * 2           // (agent, window) work items of the window filter
-             + (size_t)W * 3 * kSwQueue * 4      // per-warp near / cp / rounding-tie queues
-             + (size_t)W * 2 * 32 * 4            // pooled leftovers
+             + (size_t)W * (ties ? 3 : 2) * kSwQueue * 4   // per-warp near / cp / rounding-tie queues
+             + (uni ? 0 : (size_t)W * 2 * 32 * 4)          // pooled leftovers
              + (size_t)W * 16 * 4                // per-warp partial results
              + nW * 16                           // ego window boxes
-             + (size_t)T * (16 + 8)              // egoA, egoB
+             + (size_t)T * (16 + 8 + 16)         // egoA, egoB, BE segment slopes
              + (size_t)((T + 3) & ~3) * 4        // dist
              + nW * 4;                           // ego window speeds
   return (b + 15) & ~(size_t)15;
@@ -73,6 +78,7 @@ struct SweepSmem {
   float4* egoA;                 // [T] (x, y, cos theta, sin theta)
   float2* egoB;                 // [T] (theta, v)
   float* dist;                  // [T] cumulative chord length (BE)
+  float4* seg;                  // [T] BE segment slopes (BeView::seg)
   uint32_t* colfirst;           // [kSwTile] first step with rounded distance 0
   uint32_t* q_near;             // [W][kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
   uint32_t* q_cp;               // [W][kSwQueue] (agent-in-tile << 8 | step)
@@ -90,7 +96,7 @@ struct SweepSmem {
 
 // Fixed-size arrays first, then the per-warp ones, then the T-sized ones: every hot array except egoB / dist sits at
 // a compile-time offset when W is a constant (the one-warp throughput shape), so its address is an immediate.
-__device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int W) {
+__device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int W, bool uni, bool ties) {
   SweepSmem w;
   w.pairkey = reinterpret_cast<unsigned long long*>(base);
   w.colfirst = reinterpret_cast<uint32_t*>(w.pairkey + kSwTile);
@@ -101,12 +107,13 @@ __device__ __forceinline__ SweepSmem sweep_smem(unsigned char* base, int T, int 
   w.q_near = reinterpret_cast<uint32_t*>(w.q_win + kSwWinQueue);
   w.q_cp = w.q_near + (size_t)W * kSwQueue;
   w.q_tie = w.q_cp + (size_t)W * kSwQueue;
-  w.pool_near = w.q_tie + (size_t)W * kSwQueue;
-  w.pool_cp = w.pool_near + (size_t)W * 32;
-  w.red = reinterpret_cast<float*>(w.pool_cp + (size_t)W * 32);
+  w.pool_near = w.q_tie + (ties ? (size_t)W * kSwQueue : 0);
+  w.pool_cp = w.pool_near + (uni ? 0 : (size_t)W * 32);
+  w.red = reinterpret_cast<float*>(w.pool_cp + (uni ? 0 : (size_t)W * 32));
   w.ew = reinterpret_cast<float4*>(w.red + (size_t)W * 16);
   w.egoA = w.ew + agent_windows(T);
-  w.egoB = reinterpret_cast<float2*>(w.egoA + T);
+  w.seg = w.egoA + T;
+  w.egoB = reinterpret_cast<float2*>(w.seg + T);
   w.dist = reinterpret_cast<float*>(w.egoB + T);
   w.evw = w.dist + ((T + 3) & ~3);
   return w;
@@ -182,7 +189,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, wib = tid >> 5, W = nthr >> 5;
   const int T = k.T;
-  const SweepSmem w = sweep_smem(smem_raw, T, UNI ? 1 : W);
+  const SweepSmem w = sweep_smem(smem_raw, T, UNI ? 1 : W, UNI, TIES);
   uint32_t* const q_near = w.q_near + wib * kSwQueue;
   uint32_t* const q_cp = w.q_cp + wib * kSwQueue;
   uint32_t* const q_tie = w.q_tie + wib * kSwQueue;
@@ -194,7 +201,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
   const float cmax = fmaxf(0.0f, fmaxf(k.hc.rs_side, k.hc.rs_rear));
   const int Ap = k.tab.Ap;
   const auto soff = [&](const void* q) { return (uint32_t)(reinterpret_cast<const unsigned char*>(q) - smem_raw); };
-  const BeView bev{soff(w.egoA), soff(w.egoB), soff(w.dist), soff(w.inv)};
+  const BeView bev{soff(w.egoA), soff(w.egoB), soff(w.dist), soff(w.inv), soff(w.seg)};
   const BeConst bek = be_const(k);
   // lane -> (agent within the lane group, time slice); every (warp, slice) owns a contiguous range of steps
   const int lg = shape.lg_agents;
@@ -602,7 +609,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const int n_be = (int)w.scal[1];
         if (n_be > 0) {
           if (!be_ready) {
-            if (wib == 0) be_prepare(bev, T, lane);
+            if (wib == 0) be_prepare<true>(bev, T, lane);
             __syncthreads();
             be_ready = true;
           }
@@ -610,7 +617,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
           for (int q = wib; q < n_be; q += W) {        // bisections dealt round-robin to the warps
             const int a = a0 + (int)w.be_list[q];
             const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
-            const float2 be = be_bisect(bek, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane);
+            const float2 be = be_bisect<true>(bek, bev, a, pa.x, __int_as_float(pa.z), __int_as_float(pa.w), be_lo0, lane);
             const float rcd = be.x;
             if (rcd != rcd) flags |= FO_F_BE_RANGE;      // NaN: the re-timed path overruns the planned one
             rcd_all = fmaxf(rcd_all, rcd);
@@ -761,7 +768,7 @@ static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st)
 
 template <uint32_t MASK, bool STATS, bool UNI, bool TIES>
 static int launch_sweep_shape(const MetricKArgs& k, int num_sms, int W, const SweepShape& shape, cudaStream_t st) {
-  const size_t smem = sweep_smem_bytes(k.T, W);
+  const size_t smem = sweep_smem_bytes(k.T, W, UNI, TIES);
   // the opt-in shared-memory size is a per-device function attribute: remember what each device has been given
   static std::atomic<size_t> configured[kMaxDev];
   int dev = 0;

@@ -9,7 +9,7 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CSRC=$ROOT/frenetix_occlusion_b200/csrc
-ALL="fo_metric fo_metric_detail fo_metric_sweep fo_visibility fo_points fo_rollout fo_capi"
+ALL="fo_metric fo_metric_detail fo_metric_sweep fo_visibility fo_points fo_spawn fo_rollout fo_capi"
 case "$1" in
   build)
     shift; src=$1; shift; i=${AB_FIRST:-1}; i=$((i - 1))     # AB_FIRST=5: number the variants from 5 on
