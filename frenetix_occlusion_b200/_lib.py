@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("FO_LIB_PATH") or os.path.join(_HERE, "libfo_b200.so")
 
 FO_OK = 0
 FO_MAX_STATES = 128
+FO_MAX_PEERS = 8
 FO_SUMMARY_K = 10
 FO_PAIR_K = 12
 FO_STEP_K = 3
@@ -57,7 +58,12 @@ class FoMetricArgs(C.Structure):
                 ("thr_harm", C.c_double), ("thr_risk", C.c_double), ("thr_be", C.c_double),
                 ("thr_cp", C.c_double), ("thr_ttc", C.c_double), ("thr_dce", C.c_double),
                 ("valid", C.c_void_p), ("summary", C.c_void_p), ("flags", C.c_void_p),
-                ("pair", C.c_void_p), ("step", C.c_void_p)]
+                ("pair", C.c_void_p), ("step", C.c_void_p),
+                ("n_peers", C.c_int32), ("reserved_", C.c_int32), ("peer_delta", C.c_int64 * FO_MAX_PEERS)]
+
+
+class FoPeerHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64)]
 
 
 class FoVisibilityArgs(C.Structure):
@@ -152,6 +158,10 @@ _PROTOS = {
     "fo_spawn_rect": (C.c_int, [C.POINTER(FoSpawnRectArgs), C.c_void_p]),
     "fo_rollout_cv": (C.c_int, [C.POINTER(FoRolloutCvArgs), C.c_void_p]),
     "fo_rollout_path": (C.c_int, [C.POINTER(FoRolloutPathArgs), C.c_void_p]),
+    "fo_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(FoPeerHandle)]),
+    "fo_peer_open": (C.c_int, [C.POINTER(FoPeerHandle), C.POINTER(C.c_void_p)]),
+    "fo_peer_close": (C.c_int, [C.c_void_p]),
+    "fo_peer_free": (C.c_int, [C.c_void_p]),
     "fo_probe_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),
     "fo_launch_count": (C.c_uint64, []),
     "fo_version": (C.c_int, []),

@@ -66,6 +66,44 @@ extern "C" int fo_version(void) { return FO_ABI_VERSION; }
 extern "C" const char* fo_last_error(void) { return fo::g_err; }
 extern "C" uint64_t fo_launch_count(void) { return fo::g_launches.load(std::memory_order_relaxed); }
 
+// ---- peer-mapped buffers (CUDA IPC) ---------------------------------------------------------------------------------
+static_assert(sizeof(FoPeerHandle) == sizeof(cudaIpcMemHandle_t), "FoPeerHandle carries a cudaIpcMemHandle_t");
+
+extern "C" int fo_peer_alloc(size_t bytes, void** dev_ptr, FoPeerHandle* handle) {
+  if (!dev_ptr || !handle || bytes == 0) { fo::set_error("fo_peer_alloc: bad argument"); return FO_ERR_INVALID_ARG; }
+  void* p = nullptr;
+  FO_CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    fo::set_error("fo_peer_alloc: %s", cudaGetErrorString(e));
+    return FO_ERR_CUDA;
+  }
+  memcpy(handle->bytes, &h, sizeof(h));
+  *dev_ptr = p;
+  return FO_OK;
+}
+
+extern "C" int fo_peer_open(const FoPeerHandle* handle, void** dev_ptr) {
+  if (!dev_ptr || !handle) { fo::set_error("fo_peer_open: bad argument"); return FO_ERR_INVALID_ARG; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle->bytes, sizeof(h));
+  FO_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FO_OK;
+}
+
+extern "C" int fo_peer_close(void* dev_ptr) {
+  if (dev_ptr) FO_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return FO_OK;
+}
+
+extern "C" int fo_peer_free(void* dev_ptr) {
+  if (dev_ptr) FO_CUDA_TRY(cudaFree(dev_ptr));
+  return FO_OK;
+}
+
 extern "C" int fo_probe_fp32_peak(int32_t iters, float* ms, double* flops, void* stream) {
   if (iters <= 0 || !ms || !flops) { fo::set_error("fo_probe_fp32_peak: bad argument"); return FO_ERR_INVALID_ARG; }
   int dev = 0, sms = 0;

@@ -224,6 +224,11 @@ static int metric_bundle_impl(const FoMetricArgs* a, unsigned long long* stats, 
   k.stats = stats;
   { const char* e = getenv("FO_EXACT_DCE"); k.exact_dce = e && e[0] == '1'; }
   k.claim = nullptr;
+  if (a->summary && (reinterpret_cast<uintptr_t>(a->summary) & 7u)) { fo::set_error("fo_metric_bundle: summary must be 8-byte aligned"); return FO_ERR_INVALID_ARG; }
+  if (a->n_peers < 0 || a->n_peers > FO_MAX_PEERS) { fo::set_error("fo_metric_bundle: n_peers %d outside [0, %d]", a->n_peers, FO_MAX_PEERS); return FO_ERR_INVALID_ARG; }
+  if (a->n_peers > 0 && (a->pair || a->step || stats)) { fo::set_error("fo_metric_bundle: peer stores exist on the summary path only"); return FO_ERR_UNSUPPORTED; }
+  k.n_peers = a->n_peers;
+  for (int p = 0; p < FO_MAX_PEERS; ++p) k.peer_delta[p] = p < a->n_peers ? (long long)a->peer_delta[p] : 0;
 
   cudaStream_t st = (cudaStream_t)stream;
   if (k.pair || k.step) return fo::launch_metric_detail(k, g_num_sms, st);

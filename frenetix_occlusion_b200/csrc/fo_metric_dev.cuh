@@ -35,6 +35,8 @@ struct MetricKArgs {
   float* step;
   unsigned long long* stats;   // optional [8] work counters (see fo_metric_stats), NULL in production launches
   unsigned int* claim;         // zeroed per launch: next-trajectory counter of the summary kernel (NULL = static striding)
+  int n_peers;                 // summary kernel: results are also stored at these byte offsets (peer-mapped gather buffers)
+  long long peer_delta[FO_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------------------------

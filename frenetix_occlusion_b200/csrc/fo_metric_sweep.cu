@@ -667,15 +667,24 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (do_dce && (k.tmask & FO_T_DCE) && rmin_t != 0xffffffu && rmin_t < k.thr_dce_mm) ok = false;
         if (fl & FO_F_BE_RANGE) ok = false;
       }
-      k.valid[n] = ok ? 1 : 0;
-      if (k.flags) k.flags[n] = fl;
-      if (k.summary) {
-        float* sm = k.summary + (size_t)n * FO_SUMMARY_K;
-        sm[0] = er; sm[1] = orr; sm[2] = do_hr ? eh : 0.0f; sm[3] = do_hr ? oh : 0.0f; sm[4] = cpm; sm[5] = hwc_all;
-        sm[6] = (rmin_t == 0xffffffu || !do_dce) ? CUDART_INF_F : mm_to_m(rmin_t);
-        sm[7] = has_col ? step_to_s(col, k.dtd) : CUDART_INF_F;
-        sm[8] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : btn;
-        sm[9] = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd;
+      const float o6 = (rmin_t == 0xffffffu || !do_dce) ? CUDART_INF_F : mm_to_m(rmin_t);
+      const float o7 = has_col ? step_to_s(col, k.dtd) : CUDART_INF_F;
+      const float o8 = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : btn, o9 = (fl & FO_F_BE_RANGE) ? CUDART_NAN_F : rcd;
+      // Fused result exchange of a sharded sweep: the same stores go to this rank's slice of every peer's gather buffer
+      // (peer-mapped device memory, NVLink); p = -1 is the local copy.  Rows are 40 bytes: five 8-byte stores.
+#pragma unroll 1
+      for (int p = -1; p < k.n_peers; ++p) {
+        const long long dl = p < 0 ? 0ll : k.peer_delta[p];
+        reinterpret_cast<uint8_t*>(reinterpret_cast<char*>(k.valid) + dl)[n] = ok ? 1 : 0;
+        if (k.flags) reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(k.flags) + dl)[n] = fl;
+        if (k.summary) {
+          float2* sm = reinterpret_cast<float2*>(reinterpret_cast<char*>(k.summary) + dl) + (size_t)n * (FO_SUMMARY_K / 2);
+          sm[0] = make_float2(er, orr);
+          sm[1] = make_float2(do_hr ? eh : 0.0f, do_hr ? oh : 0.0f);
+          sm[2] = make_float2(cpm, hwc_all);
+          sm[3] = make_float2(o6, o7);
+          sm[4] = make_float2(o8, o9);
+        }
       }
     }
     n = s_next;

@@ -135,6 +135,7 @@ class BundleResult:
     flags: torch.Tensor                # int32 [N]
     pair: Optional[torch.Tensor] = None   # float32 [N, A, FO_PAIR_K]
     step: Optional[torch.Tensor] = None   # float32 [N, A, T-1, FO_STEP_K]
+    peer_delta: Optional[Sequence[int]] = None   # byte offsets to the peer-mapped copies of valid / summary / flags (parallel.py)
 
 
 class MetricEngine:
@@ -240,6 +241,11 @@ class MetricEngine:
             v = self.thresholds.get(name)
             setattr(a, "thr_" + name, float(v) if v is not None else 0.0)
         a.valid, a.summary, a.flags = out.valid.data_ptr(), out.summary.data_ptr(), out.flags.data_ptr()
+        deltas = out.peer_delta                        # parallel.PeerResultGatherer: fused result exchange
+        if deltas:
+            a.n_peers = len(deltas)
+            for i, d in enumerate(deltas):
+                a.peer_delta[i] = int(d)
         return a
 
     def work_stats(self, ego) -> dict:

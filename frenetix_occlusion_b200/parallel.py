@@ -75,7 +75,10 @@ class ResultGatherer:
         self.off_flags = _align(cap)
         self.off_summary = self.off_flags + _align(4 * cap)
         self.slice_bytes = self.off_summary + _align(4 * summary_k * cap)
-        self.full = torch.zeros(self.slice_bytes * self.world, dtype=torch.uint8, device=device)
+        self.full = self._alloc(self.slice_bytes * self.world, device)
+
+    def _alloc(self, nbytes: int, device):
+        return torch.zeros(nbytes, dtype=torch.uint8, device=device)
 
     # ---- views ------------------------------------------------------------------------------------------------
     def _views(self, r: int):
@@ -93,6 +96,11 @@ class ResultGatherer:
         from .engine import BundleResult
         v, s, f = self._views(self.rank)
         return BundleResult(v, s, f)
+
+    def slice_of(self, result, lo: int, hi: int):
+        """``result[lo:hi]`` as a ``BundleResult`` of its own (chunked evaluation into one gather buffer)."""
+        from .engine import BundleResult
+        return BundleResult(result.valid[lo:hi], result.summary[lo:hi], result.flags[lo:hi], peer_delta=result.peer_delta)
 
     def rank_result(self, r: int):
         """(valid, summary, flags) views of rank ``r``'s shard after ``gather()`` (local order of ``index[r]``)."""
@@ -132,3 +140,100 @@ class ResultGatherer:
             v, s, f = self._views(r)
             valid[idx], summary[idx], flags[idx] = v, s, f
         return valid, summary, flags
+
+
+class _DeviceBytes:
+    """Raw device memory as a ``__cuda_array_interface__`` object (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerResultGatherer(ResultGatherer):
+    """The exchange step FUSED into the metric kernel (optional form): no all-gather at all.
+
+    Every rank's gather buffer is CUDA-IPC device memory (``fo_peer_alloc``) mapped into every other rank's process
+    (``fo_peer_open``); ``local_result()`` carries the address differences as ``peer_delta``, and the summary kernel's
+    epilogue stores valid / summary / flags of each trajectory into this rank's slice of ALL buffers -- the remote
+    copies travel over NVLink / NVSwitch while the rest of the bundle is still being evaluated.  What is left of the
+    collective is a completion handshake (``gather()``: one 4-byte all-reduce, stream-ordered behind the kernel).
+
+    Two buffers alternate between steps: rank A's kernel of step k + 1 may start while rank B still reads the results
+    of step k (its D2H copy, a consumer kernel) -- it writes the other buffer; by the time step k + 2 reuses the first
+    one, every rank has passed the handshake of step k + 1, which its own stream ordered behind its reads of step k."""
+
+    def __init__(self, n_total: int, summary_k: int, device, group=None, block: Optional[int] = 1024):
+        from . import _lib as L
+        import ctypes as C
+        self._L, self._C = L, C
+        self._own, self._mapped = [], []
+        self._phase, self._gathered = 0, False
+        self._device = torch.device(device)
+        super().__init__(n_total, summary_k, device, group=group, block=block)   # allocates buffer 0 (self.full)
+        self._bufs = [self.full, self._alloc(self.slice_bytes * self.world, device)]
+        # exchange the handles, map the peers' buffers, keep the address differences
+        mine = [bytes(h.bytes) for _, h in self._own]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._delta = [[], []]
+        for r, handles in enumerate(everyone):
+            if r == self.rank:
+                continue
+            for b, raw in enumerate(handles):
+                h = L.FoPeerHandle()
+                C.memmove(h.bytes, raw, 64)
+                ptr = C.c_void_p()
+                L.check(L.lib.fo_peer_open(C.byref(h), C.byref(ptr)), "fo_peer_open")
+                self._mapped.append(ptr.value)
+                self._delta[b].append(ptr.value - self._own[b][0])
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._nccl = dist.get_backend(self.group) == "nccl"
+        self._results = [None, None]
+
+    def _alloc(self, nbytes: int, device):
+        L, C = self._L, self._C
+        ptr, h = C.c_void_p(), L.FoPeerHandle()
+        with torch.cuda.device(self._device):
+            L.check(L.lib.fo_peer_alloc(nbytes, C.byref(ptr), C.byref(h)), "fo_peer_alloc")
+            t = torch.as_tensor(_DeviceBytes(ptr.value, nbytes), device=self._device)
+        self._own.append((ptr.value, h))
+        return t
+
+    def local_result(self):
+        """This step's output views (+ ``peer_delta``).  The first call after a ``gather()`` moves on to the other buffer."""
+        if self._gathered:
+            self._phase ^= 1
+            self._gathered = False
+        self.full = self._bufs[self._phase]
+        if self._results[self._phase] is None:
+            r = super().local_result()
+            r.peer_delta = list(self._delta[self._phase])
+            self._results[self._phase] = r
+        return self._results[self._phase]
+
+    def gather(self, valid=None, summary=None, flags=None):
+        """Completion handshake: when it has passed on this rank's stream, every rank's kernel of the step has finished
+        and with it the stores into this rank's buffer."""
+        if valid is not None:
+            raise ValueError("the fused exchange has no copy-in form: evaluate into local_result()")
+        if self.world > 1:
+            if self._nccl:
+                dist.all_reduce(self._flag, group=self.group)
+            else:       # host-level handshake (gloo in the tests)
+                torch.cuda.synchronize(self._device)
+                dist.barrier(group=self.group)
+        self._gathered = True
+        return self
+
+    def close(self):
+        L = self._L
+        torch.cuda.synchronize(self._device)
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)       # nobody still writes into a buffer that is about to go away
+        for p in self._mapped:
+            L.lib.fo_peer_close(p)
+        self._mapped = []
+        self._results, self._bufs, self.full = [None, None], [], None
+        for p, _ in self._own:
+            L.lib.fo_peer_free(p)
+        self._own = []

@@ -99,6 +99,7 @@ size_t fo_agent_table_bytes(int32_t n_agents, int32_t t_stride);
 int fo_agents_pack(const FoAgentsRaw *raw, const FoVehicle *vehicle, void *table_dev, size_t table_bytes,
                    void *stream);
 
+#define FO_MAX_PEERS 8
 #define FO_SUMMARY_K 10
 /* summary[n, :] = { max_ego_risk_all, max_obst_risk_all, max_ego_harm_all, max_obst_harm_all,
  *                   max_collision_probability_all, max_obst_harm_with_cp_all   (hr.py:108-114),
@@ -131,10 +132,17 @@ typedef struct FoMetricArgs {
   double thr_harm, thr_risk, thr_be, thr_cp, thr_ttc, thr_dce;  /* strict > / < as metric.py:55-98 */
   /* ---- outputs (device; optional ones may be NULL) --------------------------------------------- */
   uint8_t *valid;          /* [N] safety_check of Metric.evaluate_metrics */
-  float *summary;          /* [N, FO_SUMMARY_K] */
+  float *summary;          /* [N, FO_SUMMARY_K], 8-byte aligned */
   uint32_t *flags;         /* [N] FO_F_* */
   float *pair;             /* [N, A, FO_PAIR_K] or NULL; 16-byte aligned */
   float *step;             /* [N, A, T-1, FO_STEP_K] or NULL */
+  /* ---- fused result exchange of a trajectory-sharded sweep (summary path only) ------------------- */
+  int32_t n_peers;         /* 0 = none.  Otherwise the kernel's epilogue stores valid / summary / flags of every trajectory
+                              ALSO at the same addresses shifted by peer_delta[p] bytes: the mapped buffers of the other
+                              ranks (fo_peer_open), reached over NVLink.  This rank's slice of every rank's gather buffer
+                              is complete when the launch has finished; no all-gather follows. */
+  int32_t reserved_;
+  int64_t peer_delta[FO_MAX_PEERS];
 } FoMetricArgs;
 
 /* Stage 3, the dense core: every trajectory x every phantom prediction x every step.
@@ -332,6 +340,18 @@ typedef struct FoSpawnRectArgs {
 } FoSpawnRectArgs;
 
 int fo_spawn_rect(const FoSpawnRectArgs *args, void *stream);
+
+/* ---- peer-mapped result buffers (multi-GPU sweeps, one process per GPU) --------------------------------
+ * The single exchange step of the sharded path (one all-gather of valid / summary / flags) fused into the
+ * metric kernel: every rank allocates its gather buffer with fo_peer_alloc, passes the handle to the other ranks (any
+ * host channel; the Python host uses torch.distributed.all_gather_object), maps theirs with fo_peer_open and hands the
+ * address differences to fo_metric_bundle as FoMetricArgs.peer_delta.  Buffers are plain device memory for every other
+ * purpose.  CUDA IPC underneath: one process per GPU on one node, peer access over NVLink / NVSwitch. */
+typedef struct FoPeerHandle { uint8_t bytes[64]; } FoPeerHandle;
+int fo_peer_alloc(size_t bytes, void **dev_ptr, FoPeerHandle *handle);   /* zero-filled */
+int fo_peer_open(const FoPeerHandle *handle, void **dev_ptr);            /* another process's buffer, mapped here */
+int fo_peer_close(void *dev_ptr);                                        /* unmap (fo_peer_open) */
+int fo_peer_free(void *dev_ptr);                                         /* release (fo_peer_alloc) */
 
 /* ---- stage 2: phantom-agent rollouts ---------------------------------------------------------------
  * Constant-velocity pedestrian prediction: OAPPedestrianAgent._create_ped_trajectory (agent.py:451-505)
