@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kDtWarps * 32, FO_DT_MINB) fo_metric_detail_ke
           todo &= todo - 1;
           const int ns_s = __shfl_sync(kFull, P.n_states, src);
           const float hl_s = __shfl_sync(kFull, P.hl, src), hw_s = __shfl_sync(kFull, P.hw, src);
-          const float r = be_bisect<false>(bek, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane).x;
+          const float r = be_bisect<false>(bek, bev, a0 + src, ns_s, hl_s, hw_s, be_lo0, lane, -1.0f).x;
           if (r != r) flags |= FO_F_BE_RANGE;            // NaN: the re-timed path overruns the planned one
           if (lane == src) { rcd = r; btn = __fdividef(r, k.a_max); }
         }

@@ -349,9 +349,14 @@ __device__ __forceinline__ float be_arclen(float dt, float v0, float v1, float s
 
 // Returns (required constant deceleration, number of probes as int bits); the deceleration is NaN when the re-timed
 // path overruns the planned one (the reference raises, be.py:117-124).
+// floor_rcd (summary kernel; negative = off): the caller keeps only the MAXIMUM over a trajectory's pairs.  The bracket
+// [lo, hi] only shrinks and the result is its last midpoint, so once hi <= floor_rcd this pair cannot raise the maximum
+// and the bisection stops -- provided no later probe could overrun the planned path: dist_new[T-1] falls with the
+// deceleration, the smallest deceleration the rest of the bisection can probe is the end of its all-miss branch, and
+// that one is checked (with a margin for the float32 closed form; inside the margin the bisection simply runs on).
 template <bool SEG>
 static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v, int a, int n_states, float hl, float hw,
-                                                float lo0, int lane) {
+                                                float lo0, int lane, float floor_rcd) {
   extern __shared__ __align__(16) unsigned char fo_dyn_smem[];
   const float4* const egoA = reinterpret_cast<const float4*>(fo_dyn_smem + v.egoA);
   const float2* const egoB = reinterpret_cast<const float2*>(fo_dyn_smem + v.egoB);
@@ -428,6 +433,17 @@ static __device__ __noinline__ float2 be_bisect(const BeConst k, const BeView v,
     }
     if (nA > 0 && !any_hit) hi = cur; else lo = cur;   // be.py:74-77 (an agent that never exists counts as a hit)
     if (hi - lo < 0.1f) break;                         // be.py:79
+    if (hi <= floor_rcd) {
+      float h = hi, c = cur;
+      for (int j = it + 1; j < 10; ++j) {              // the all-miss branch of what is left, same arithmetic
+        c = 0.5f * (lo + h);
+        h = c;
+        if (h - lo < 0.1f) break;
+      }
+      const float st = c * k.dt;
+      const float mp = (st > 0.0f) ? fmaxf(floorf(v1 * rcp_approx(st)) + 1.0f, 0.0f) : 1.0e9f;
+      if (be_arclen(k.dt, v0, v1, st, mp, T - 1) < dmax * 0.99999f) break;
+    }
   }
   return make_float2(cur, __int_as_float(probes));
 }
