@@ -614,19 +614,6 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
             be_ready = true;
           }
           const float be_lo0 = rintf(__uint_as_float(w.scal[0]) * 100.0f) / 100.0f;   // be.py:68
-#ifdef FO_BE_ORDER
-          // the pair that collides first usually needs the hardest braking: bisected first, it sets the floor that
-          // cuts the other bisections short (any order gives the same maximum)
-          if (W == 1 && n_be > 1) {
-            uint32_t best = 0xffffffffu;
-            for (int q = lane; q < n_be; q += 32) best = min(best, (w.colfirst[w.be_list[q]] << 16) | (uint32_t)q);
-            best = __reduce_min_sync(kFull, best);
-            const int qb = (int)(best & 0xffffu);
-            __syncwarp();
-            if (lane == 0 && qb != 0) { const uint16_t t0 = w.be_list[0]; w.be_list[0] = w.be_list[qb]; w.be_list[qb] = t0; }
-            __syncwarp();
-          }
-#endif
           // only max over the pairs is kept: a bisection stops as soon as its bracket lies below the running maximum
           // (be_bisect), and a range error makes every further one moot (the outputs are NaN, the trajectory invalid)
           for (int q = wib; q < n_be && !(flags & FO_F_BE_RANGE); q += W) {   // bisections dealt round-robin to the warps
