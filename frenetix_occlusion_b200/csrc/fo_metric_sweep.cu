@@ -186,8 +186,10 @@ template <uint32_t MASK, bool STATS, bool UNI, bool TIES>
 __global__ void __launch_bounds__(kSwMaxWarps * 32, FO_SW_MINB)
 fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape shape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int lane = tid & 31, wib = tid >> 5, W = nthr >> 5;
+  // the one-warp shape is launched with 32 threads: warp index, team size and lane are compile-time facts there (the
+  // queue addresses become immediates instead of being re-derived from %tid wherever registers are short)
+  const int tid = threadIdx.x, nthr = UNI ? 32 : blockDim.x;
+  const int lane = UNI ? tid : (tid & 31), wib = UNI ? 0 : (tid >> 5), W = UNI ? 1 : (nthr >> 5);
   const int T = k.T;
   const SweepSmem w = sweep_smem(smem_raw, T, UNI ? 1 : W, UNI, TIES);
   uint32_t* const q_near = w.q_near + wib * kSwQueue;
