@@ -286,8 +286,8 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         float t2 = CUDART_INF_F;
         if (is_m1) {
           const float ze_m = fmaxf(zb_e, acc_ze), zo_m = fmaxf(zb_o, acc_zo);
-          const float te = (kse > 0.0f) ? __fdividef(ze_m - cmax - kce, kse) : ((kce + cmax > ze_m) ? -1.0f : CUDART_INF_F);
-          const float to = (kso > 0.0f) ? __fdividef(zo_m - cmax - kco, kso) : ((kco + cmax > zo_m) ? -1.0f : CUDART_INF_F);
+          const float te = (kse > 1e-30f) ? (ze_m - cmax - kce) * rcp_approx(kse) : ((kce + cmax > ze_m) ? -1.0f : CUDART_INF_F);
+          const float to = (kso > 1e-30f) ? (zo_m - cmax - kco) * rcp_approx(kso) : ((kco + cmax > zo_m) ? -1.0f : CUDART_INF_F);
           const float tm = fminf(te, to);
           t2 = (tm > 0.0f) ? tm * tm * 0.99999f : -1.0f;
         }
@@ -414,18 +414,18 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const uint32_t item0 = (uint32_t)al << 8;
         // time-major table, agents padded to a multiple of 32: the agent index is always in bounds; rows are only
         // read for steps the agent has (i < n_states <= t_stride)
-        const float4* t0 = k.tab.t0 + (size_t)i_lo * Ap + a;
-        const float* tv = k.tab.tv + (size_t)i_lo * Ap + a;
+        // one 32-bit element offset into both time-major arrays (base pointers are kernel arguments: uniform registers)
+        uint32_t toff = (uint32_t)(i_lo * Ap + a);
         float pxp = 0.0f, pyp = 0.0f;                      // position at i-1 (collision_probability.py:52)
-        if (do_cp && i_lo >= 1 && i_lo < nS) { const float4 sp = __ldg(t0 - Ap); pxp = sp.x; pyp = sp.y; }
+        if (do_cp && i_lo >= 1 && i_lo < nS) { const float4 sp = __ldg(k.tab.t0 + (toff - (uint32_t)Ap)); pxp = sp.x; pyp = sp.y; }
         float acc_dv2 = -1.0f;                             // unprotected agents: max_t logit = ks sqrt(max_t dv^2) + kc
         int i = i_lo;
 #pragma unroll kSwUnroll
-        for (int r = 0; r < n_it; ++r, ++i, t0 += Ap, tv += Ap) {
+        for (int r = 0; r < n_it; ++r, ++i, toff += (uint32_t)Ap) {
           const bool live = i < nS;
           float4 s0 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
           float va = 0.0f;
-          if (live) { s0 = __ldg(t0); va = __ldg(tv); }
+          if (live) { s0 = __ldg(k.tab.t0 + toff); va = __ldg(k.tab.tv + toff); }
           const int ie = min(i, T - 1);
           const float4 EA = w.egoA[ie];
           const float ve = w.egoB[ie].y;
@@ -516,8 +516,8 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
                 const float fce = (m0 ? k.hc.ia_const : k.hc.rs_const) + cm;
                 const float fco = (m0 ? -k.hc.ped_const : k.hc.rs_const) + cm;
                 const float ze_m = fmaxf(zb_e, acc_ze), zo_m = fmaxf(zb_o, acc_zo);
-                const float te = (fse > 0.0f) ? __fdividef(ze_m - fce, fse) : ((fce > ze_m) ? -1.0f : CUDART_INF_F);
-                const float to = (fso > 0.0f) ? __fdividef(zo_m - fco, fso) : ((fco > zo_m) ? -1.0f : CUDART_INF_F);
+                const float te = (fse > 1e-30f) ? (ze_m - fce) * rcp_approx(fse) : ((fce > ze_m) ? -1.0f : CUDART_INF_F);
+                const float to = (fso > 1e-30f) ? (zo_m - fco) * rcp_approx(fso) : ((fco > zo_m) ? -1.0f : CUDART_INF_F);
                 const float tm = fminf(te, to);
                 t2 = (tm > 0.0f) ? tm * tm * 0.99999f : -1.0f;
               }
