@@ -446,7 +446,7 @@ def run_ours(args):
                 "hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
                         "peak_source": hbm_src},
-                "note": "the summary kernel is instruction-issue bound (ncu: issue slots 80 % busy, FMA pipe 37 %), not "
+                "note": "the summary kernel is instruction-issue bound (ncu: issue slots 84 % busy, FMA pipe 36 %, ALU 45 %, XU 22 %; profiles/ncu_r2_sweep_summary.txt), not "
                         "FP32- or HBM-bound: frac counts only flops it executes; effective_frac charges every "
                         "(traj, agent, step) evaluation at the algorithmic cost although exact bounds skip 80 % of them, "
                         "so it measures pruning, not pipe utilisation"}
