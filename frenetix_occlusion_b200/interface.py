@@ -90,7 +90,7 @@ class FOInterface:
         road = [np.array([[-1.0, -2.0], [30.0, -2.0], [30.0, 4.0], [-1.0, 4.0]])]
         fr = FrameGeometry([0.0, 0.0], 0.0, np.array([[8.0, 0.5, 0.1, 2.0, 1.0]]), np.array([1], dtype=np.uint8),
                            np.array([[0.0, 4.0, 30.0, 4.0]]), road, self.sensor_radius, self.sensor_angle, device=self.device)
-        fr.raycast_host(self.sensor_model.n_rays)
+        fr.raycast_host(self.sensor_model.n_rays, road_hits=(0.0, 2.0 * np.pi / self.sensor_model.n_rays))
         fr.classify(np.array([[3.0, 1.0], [15.0, 0.5]]), focus_obstacle=0, focus_margin=1.0)
         rollout_cv([1.0], [1.0], [1.4], [0.3], self.dt, 3.0, device=self.device)
         rollout_path([np.array([[0.0, 0.0], [20.0, 0.0], [40.0, 1.0]])], [2.0], [0.2], [5.0], self.dt, 3.0, device=self.device)

@@ -134,8 +134,25 @@ class SensorModel:
         return FrameGeometry(self.ego_pos, self.ego_orientation, rect, flags, border, self.lanelet_polygons,
                              self.sensor_radius, self.sensor_angle, device=self.device)
 
-    def _raycast(self):
-        return self._frame.raycast_host(self.n_rays)
+    def _raycast(self, road_hits=None):
+        return self._frame.raycast_host(self.n_rays, road_hits=road_hits)
+
+    def _hits_on_road(self, rng, hit, vis, ray_lists, angles):
+        """Host restatement of ``fo_visibility_hits_on_road`` (the tests hold the kernel to it): the end points of the
+        rays that hit a seen obstacle, classified point by point."""
+        O = len(ray_lists)
+        out = np.zeros(O, dtype=np.uint8)
+        need = [k for k in range(O) if bool(vis[k]) and len(ray_lists[k])]
+        if need:
+            rays = np.concatenate([ray_lists[k] for k in need])
+            pts = self.ego_pos + (rng[rays] - 1e-3)[:, None] * np.stack((np.cos(angles[rays]), np.sin(angles[rays])), -1)
+            f, _, _ = self._classify(pts)
+            road = (f & L.PT_ON_ROAD) != 0
+            at = 0
+            for k in need:
+                out[k] = bool(road[at:at + len(ray_lists[k])].any())
+                at += len(ray_lists[k])
+        return out
 
     def _classify(self, points, focus=-1, focus_margin=0.0):
         if self._frame is None:
@@ -162,26 +179,15 @@ class SensorModel:
             border = border[near]
         self._frame = self._build_frame(rect, flags, border)
         self._obstacle_index = {o.cr_obstacle.obstacle_id: k for k, o in enumerate(obs)}
-        rng, hit, vis = self._raycast()
         a0, da = ray_angle_params(self.ego_orientation, self.sensor_angle, self.n_rays)
+        # ray cast + "which obstacles are hit on the road" in one stream-ordered pass and one read-back
+        rng, hit, vis, road = self._raycast(road_hits=(float(a0), float(da)))
         self.visible_area = VisibleArea(self, self.ego_pos, float(a0), float(da), rng, hit, self.sensor_angle >= 359.9,
                                         self.sensor_radius)
         # visible obstacles: the reference intersects each obstacle polygon with the (road-clipped) visible area
         # buffered by 1 cm (sensor_model.py:59-76); here: some ray ends on the obstacle at a point of the road
-        ang = self.visible_area.angles
-        # ray end points on every seen obstacle, classified in ONE device call
         ray_lists = [np.nonzero(hit == k)[0] for k in range(O)]
-        need = [k for k in range(O) if bool(vis[k]) and len(ray_lists[k])]
-        on_road = {}
-        if need:
-            rays = np.concatenate([ray_lists[k] for k in need])
-            pts = self.ego_pos + (rng[rays] - 1e-3)[:, None] * np.stack((np.cos(ang[rays]), np.sin(ang[rays])), -1)
-            f, _, _ = self._classify(pts)
-            road = (f & L.PT_ON_ROAD) != 0
-            at = 0
-            for k in need:
-                on_road[k] = bool(road[at:at + len(ray_lists[k])].any())
-                at += len(ray_lists[k])
+        on_road = {k: bool(road[k]) for k in range(O) if bool(vis[k]) and len(ray_lists[k])}
         for k, o in enumerate(obs):
             rays = ray_lists[k]
             seen = on_road[k] if k in on_road else bool(vis[k])

@@ -190,11 +190,14 @@ class FrameGeometry:
                               self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg,
                               n_rays, device=self.device)
 
-    def raycast_host(self, n_rays: int):
-        """Ray cast of this frame with ONE packed read-back: host arrays (range f32 [R], hit i32 [R], visible u8 [O])."""
+    def raycast_host(self, n_rays: int, road_hits=None):
+        """Ray cast of this frame with ONE packed read-back: host arrays (range f32 [R], hit i32 [R], visible u8 [O]).
+        ``road_hits = (angle0, dangle)`` of the fan (float64, world frame): ``fo_visibility_hits_on_road`` runs behind the
+        ray cast on the same stream and a fourth array comes back in the same copy -- on_road u8 [O], 1 = some ray ends
+        on the obstacle at a point inside a lanelet polygon (sensor_model.py:59-76)."""
         O, dev = self.n_obstacles, self.device
         with torch.cuda.device(dev):
-            nb = 8 * n_rays + max(O, 1)
+            nb = 8 * n_rays + 2 * max(O, 1)
             buf = torch.empty(nb, dtype=torch.uint8, device=dev)
             out = VisibilityResult(buf[:4 * n_rays].view(torch.float32).view(1, n_rays),
                                    buf[4 * n_rays:8 * n_rays].view(torch.int32).view(1, n_rays),
@@ -202,9 +205,25 @@ class FrameGeometry:
             raycast_frames(self.ego_d, self.rect_d.reshape(1, O, 5), self.flags_d.reshape(1, O),
                            self.bnd_d if self.n_boundary else None, self.sensor_radius, self.sensor_angle_deg, n_rays,
                            device=dev, out=out)
+            if road_hits is not None and O:
+                a = L.FoHitsOnRoadArgs()
+                a.n_rays, a.n_obstacles, a.n_polygons = n_rays, O, self.n_polygons
+                a.range, a.hit, a.ego = out.range.data_ptr(), out.hit.data_ptr(), self.ego_d.data_ptr()
+                a.poly_xy = self.poly_xy_d.data_ptr() if self.n_polygons else None
+                a.poly_off = self.poly_off_d.data_ptr() if self.n_polygons else None
+                a.ego_x, a.ego_y = float(self.origin[0]), float(self.origin[1])     # the frame origin is the ego position
+                a.angle0, a.dangle = float(road_hits[0]), float(road_hits[1])
+                a.org_x, a.org_y = float(self.origin[0]), float(self.origin[1])
+                a.on_road = buf[8 * n_rays + max(O, 1):].data_ptr()
+                st = torch.cuda.current_stream(dev)
+                L.check(L.lib.fo_visibility_hits_on_road(C.byref(a), C.c_void_p(st.cuda_stream)), "fo_visibility_hits_on_road")
             host = buf.cpu().numpy()          # one copy, synchronises
-        return host[:4 * n_rays].view(np.float32), host[4 * n_rays:8 * n_rays].view(np.int32), \
-            (host[8 * n_rays:8 * n_rays + O] if O else np.zeros(0, np.uint8))
+        res = (host[:4 * n_rays].view(np.float32), host[4 * n_rays:8 * n_rays].view(np.int32),
+               (host[8 * n_rays:8 * n_rays + O] if O else np.zeros(0, np.uint8)))
+        if road_hits is not None:
+            at = 8 * n_rays + max(O, 1)
+            res += ((host[at:at + O] if O else np.zeros(0, np.uint8)),)
+        return res
 
     # ---- spawn locator, behind-dynamic-obstacle finder on the device (fo_spawn_region / fo_spawn_rect) --------------
     def _frame_args(self, focus_obstacle: int, focus_margin: float):

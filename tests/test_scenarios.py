@@ -360,3 +360,41 @@ def test_device_spawn_region_equals_host_rasters(cuda_device):
     finally:
         SpawnLocator._occluded_region_raster, SpawnLocator._find_matching_rectangle = dev_region, dev_rect
     assert sum(1 for s in seen if s[0] == "region" and s[1]) >= 2 and any(s[0] == "rect" and s[1] > 0 for s in seen), seen
+
+
+@pytest.mark.gpu
+def test_device_hits_on_road_equal_host_classification(cuda_device):
+    """fo_visibility_hits_on_road (one launch behind the ray cast, read back with it) against the host restatement: the
+    end points of the rays that hit a seen obstacle, classified point by point with fo_visibility_points."""
+    from frenetix_occlusion_b200 import replay as R
+    from frenetix_occlusion_b200.interface import FOInterface
+    from frenetix_occlusion_b200.scenario import scenario_from_dict
+    from frenetix_occlusion_b200.sensor_model import SensorModel
+    seen = []
+    raycast = SensorModel._raycast
+
+    def both(self, road_hits=None):
+        rng, hit, vis, road = raycast(self, road_hits=road_hits)
+        O = len(vis)
+        ray_lists = [np.nonzero(hit == k)[0] for k in range(O)]
+        angles = road_hits[0] + road_hits[1] * np.arange(len(rng))
+        host = self._hits_on_road(rng, hit, vis, ray_lists, angles)
+        need = np.array([bool(vis[k]) and len(ray_lists[k]) > 0 for k in range(O)], dtype=bool)
+        assert np.array_equal(np.asarray(road)[need] != 0, host[need] != 0), (road, host)
+        # obstacles no ray ends on are never reported
+        assert not np.asarray(road)[~np.array([len(r) > 0 for r in ray_lists], dtype=bool)].any()
+        seen.append((int(need.sum()), int((host[need] != 0).sum())))
+        return rng, hit, vis, road
+
+    SensorModel._raycast = both
+    try:
+        for name in ("scene_scenario1.json", "scene_scenario2.json", "scene_scenario3.json"):
+            doc = _load(name)
+            random.seed(7)
+            sc = scenario_from_dict(doc["scene"])
+            ego = R.OpenLoopEgo(sc)
+            fo = FOInterface(sc, ego.reference_path, R.DEFAULT_VEHICLE, sc.dt, config_path=R.deployment_config(agents=doc["agents"]))
+            R.replay(fo, ego, doc["timesteps"], fan_kwargs=None)
+    finally:
+        SensorModel._raycast = raycast
+    assert sum(n for n, _ in seen) >= 10 and any(r < n for n, r in seen) or sum(r for _, r in seen) > 0, seen
