@@ -81,6 +81,7 @@ class FOInterface:
         construction instead of in the first planning cycle: one tiny call of every device entry point."""
         import numpy as np
         import scipy.ndimage  # noqa: F401  (the spawn locator's first use would otherwise pay the import in cycle 0)
+        import scipy.spatial  # noqa: F401  (convex hull of the candidate-box outlines)
         import torch
         from .engine import AgentSet
         from .prediction import rollout_cv, rollout_path
@@ -92,6 +93,14 @@ class FOInterface:
                            np.array([[0.0, 4.0, 30.0, 4.0]]), road, self.sensor_radius, self.sensor_angle, device=self.device)
         fr.raycast_host(self.sensor_model.n_rays, road_hits=(0.0, 2.0 * np.pi / self.sensor_model.n_rays))
         fr.classify(np.array([[3.0, 1.0], [15.0, 0.5]]), focus_obstacle=0, focus_margin=1.0)
+        # the device rasters of the dynamic-obstacle finder at the size a cycle uses: their workspace (the first
+        # torch.zeros on a device loads torch's own kernel module: 0.5 s), page-locked result buffers, kernel modules
+        from . import _lib as L
+        half, cell = self.spawn_locator.buffer_around_vehicle_from_side, self.spawn_locator.raster_cell
+        _, _, _, _, handle = fr.spawn_region(np.array([8.0, 0.5]), half, cell, int(np.ceil(2 * half / cell)), 1, L.PT_OCCLUDED,
+                                             L.PT_FOCUS_NEAR, half, np.array([14.0, 0.5]), 0, 1.0)
+        fr.spawn_rects(handle, [(np.array([14.0, 0.5]), 5.5, 2.5, False), (np.array([14.0, 0.5]), 2.0, 1.0, True)], 0.0,
+                       self.spawn_locator.rect_cell)
         rollout_cv([1.0], [1.0], [1.4], [0.3], self.dt, 3.0, device=self.device)
         rollout_path([np.array([[0.0, 0.0], [20.0, 0.0], [40.0, 1.0]])], [2.0], [0.2], [5.0], self.dt, 3.0, device=self.device)
         core = getattr(self.metrics, "_core", None)
