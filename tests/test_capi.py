@@ -44,6 +44,14 @@ def test_argument_validation_without_device():
     r = L.FoRolloutCvArgs()
     r.n_agents, r.n_states, r.t_stride = 2, 31, 8
     assert L.lib.fo_rollout_cv(C.byref(r), None) == -1              # stride < states
+    # peer-mapped buffers: argument checks come before any CUDA call
+    ptr, h = C.c_void_p(), L.FoPeerHandle()
+    assert L.lib.fo_peer_alloc(0, C.byref(ptr), C.byref(h)) == -1 and L.lib.fo_peer_alloc(64, None, C.byref(h)) == -1
+    assert L.lib.fo_peer_open(None, C.byref(ptr)) == -1 and L.lib.fo_peer_open(C.byref(h), None) == -1
+    assert L.lib.fo_peer_close(None) == 0 and L.lib.fo_peer_free(None) == 0
+    assert C.sizeof(L.FoPeerHandle) == 64 and L.FoMetricArgs.peer_delta.size == 8 * L.FO_MAX_PEERS
+    assert L.lib.fo_spawn_region(None, None) == -1 and L.lib.fo_spawn_rect(None, None) == -1
+    assert L.lib.fo_visibility_hits_on_road(None, None) == -1
 
 
 def test_engine_refuses_to_run_without_cuda():
