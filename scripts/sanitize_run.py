@@ -43,6 +43,12 @@ fr = FrameGeometry([1.0, 2.0], 0.3, rect[0].cpu().numpy().astype(np.float64) + n
                    ring + np.array([1.0, 2.0, 1.0, 2.0]), [np.array([[-30, -5], [30, -5], [30, 5], [-30, 5.0]]) + np.array([1.0, 2.0])],
                    50.0, 360.0)
 f, b, l = fr.classify(np.random.default_rng(0).uniform(-40, 40, (3000, 2)), focus_obstacle=1, focus_margin=1.0)
+from frenetix_occlusion_b200 import _lib as L  # noqa: E402
+rng_h, hit_h, vis_h, road_h = fr.raycast_host(700, road_hits=(0.3 - np.pi, 2 * np.pi / 700))
+cnt, cen, inside, ncomp, handle = fr.spawn_region(np.array([9.0, 3.0]), 12.0, 0.1, 240, 1, L.PT_OCCLUDED | L.PT_VISIBLE, L.PT_FOCUS_NEAR,
+                                                  12.0, np.array([12.0, 2.0]), 1, 1.0)
+boxes = fr.spawn_rects(handle, [(np.array([12.0, 2.0]), 5.5, 2.5, False), (np.array([12.0, 2.0]), 2.0, 1.0, True)], 0.2, 0.025)
+print("spawn", cnt, ncomp, [b[0] for b in boxes], int(road_h.sum()))
 rc = rollout_cv([0.0, 1.0], [0.0, 2.0], [1.4, 2.0], [0.1, 2.0], 0.1, 3.0)
 path = np.stack((np.linspace(-10, 100, 56), np.zeros(56)), -1)
 rp = rollout_path([path, path + 1.0], [5.0, 6.0], [0.4, 1.2], [10.0, 8.0], 0.1, 5.0)
