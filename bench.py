@@ -333,7 +333,7 @@ def run_ours(args):
     evals_total = N_total * A * (T - 1)
     ms, launches, clocks, kern_ms = timed(step_resident, args.steps, args.warmup, sample_clocks=True, per_step_events=True)
     value = evals_total * args.steps / (ms * 1e-3)
-    e2e_how = "torch: pinned H2D (chunked, overlapped) + fo_metric_bundle + all_gather + D2H, CUDA events, max over ranks"
+    e2e_how = ""
     if world == 1:
         # the reference-facing C-ABI call with HOST buffers: fo_metric_bundle_host copies the bundle and the raw
         # predictions to the device, packs the agent table, runs the kernel, copies valid/summary/flags back and
@@ -365,7 +365,48 @@ def run_ours(args):
         assert bool((host_valid.to(dev) == out.valid).all()), "C-ABI host call and device-resident call disagree"
         e2e_how = "fo_metric_bundle_host (C ABI, pinned host buffers in and out), host wall clock around the blocking call"
     else:
-        ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+        # N > 1: the same C-ABI host call per rank; its device destinations are this rank's slice of the gather buffer (and,
+        # fused, of every peer's), then the exchange step (handshake / all-gather).  Host wall clock, maximum over ranks.
+        import ctypes as C
+        ag = eng.agents
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+        keep = [f32(ag.x), f32(ag.y), f32(ag.yaw), f32(ag.v), f32(ag.var_x), f32(ag.var_y),
+                np.ascontiguousarray(ag.n_states, dtype=np.int32), np.ascontiguousarray(ag.kind, dtype=np.int32),
+                f32(ag.length), f32(ag.width), f32(ag.buf_length), f32(ag.buf_width)]
+        raw = L.FoAgentsRaw()
+        raw.n_agents, raw.t_stride = ag.n_agents, ag.t_stride
+        (raw.x, raw.y, raw.yaw, raw.v, raw.var_x, raw.var_y, raw.n_states, raw.kind, raw.length, raw.width,
+         raw.buf_length, raw.buf_width) = [a.ctypes.data for a in keep]
+        prm_cache = {}
+
+        def step_capi_n():
+            o = step_out()
+            if id(o) not in prm_cache:
+                prm_cache[id(o)] = (o, eng._args(ego_dev, o))
+            prm = prm_cache[id(o)][1]
+            L.check(L.lib.fo_metric_bundle_host(C.c_void_p(ego_host.data_ptr()), n_local, T, C.byref(raw), C.byref(prm),
+                                                C.c_void_p(host_valid.data_ptr()), C.c_void_p(host_summary.data_ptr()),
+                                                C.c_void_p(host_flags.data_ptr()), None, None), "fo_metric_bundle_host")
+            gatherer.gather()
+            torch.cuda.current_stream(dev).synchronize()
+
+        for _ in range(max(1, args.warmup // 2)):
+            step_capi_n()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_capi_n()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        assert bool((host_valid.to(dev) == gatherer.current_result().valid).all()), "host copy and gather buffer disagree"
+        e2e_how = ("fo_metric_bundle_host per rank (C ABI, pinned host shard in, results into the gather buffer and back to "
+                   "the host) + the exchange step, host wall clock, max over ranks")
+        if args.e2e_torch:
+            ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+            e2e_how = "torch: pinned H2D (chunked, overlapped) + fo_metric_bundle + exchange + D2H, CUDA events, max over ranks"
     e2e_value = evals_total * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -794,6 +835,7 @@ def main():
     ap.add_argument("--workload", default="c-sweep", choices=["c-sweep", "c-lat"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange fused into the kernel (peer-mapped buffers) or NCCL all-gather")
+    ap.add_argument("--e2e-torch", action="store_true", help="N > 1: time the e2e step on the torch path instead of the C-ABI host call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-stages", action="store_true")

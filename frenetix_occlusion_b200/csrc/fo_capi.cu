@@ -199,9 +199,18 @@ extern "C" int fo_metric_bundle_host(const float* ego_host, int32_t n_traj, int3
   FoMetricArgs m = *params;
   m.ego = d_ego; m.n_traj = n_traj; m.n_states = n_states; m.n_agents = (int32_t)A; m.t_stride = (int32_t)Tp;
   m.agent_table = d_tab;
-  m.valid = (uint8_t*)take(b_valid);
-  m.summary = (float*)take(b_sum);
-  m.flags = (uint32_t*)take(b_flags);
+  // Results go to the library's workspace -- or, when the caller names all three DEVICE destinations in `params`, there
+  // (a rank's slice of a gather buffer: n_peers / peer_delta then apply as in fo_metric_bundle), and from there to the host.
+  const bool dev_out = params->valid && params->summary && params->flags && !out_pair && !out_step;
+  uint8_t* ws_valid = (uint8_t*)take(b_valid);
+  float* ws_sum = (float*)take(b_sum);
+  uint32_t* ws_flags = (uint32_t*)take(b_flags);
+  if (dev_out) {
+    m.valid = params->valid; m.summary = params->summary; m.flags = params->flags;
+  } else {
+    m.valid = ws_valid; m.summary = ws_sum; m.flags = ws_flags;
+    m.n_peers = 0;
+  }
   m.pair = out_pair ? (float*)take(b_pair) : nullptr;
   m.step = (out_step && T > 1) ? (float*)take(b_step) : nullptr;
   if (A > 0) {

@@ -97,6 +97,10 @@ class ResultGatherer:
         v, s, f = self._views(self.rank)
         return BundleResult(v, s, f)
 
+    def current_result(self):
+        """The views the last step was evaluated into (never moves on to another buffer)."""
+        return self.local_result()
+
     def slice_of(self, result, lo: int, hi: int):
         """``result[lo:hi]`` as a ``BundleResult`` of its own (chunked evaluation into one gather buffer)."""
         from .engine import BundleResult
@@ -210,6 +214,10 @@ class PeerResultGatherer(ResultGatherer):
             r.peer_delta = list(self._delta[self._phase])
             self._results[self._phase] = r
         return self._results[self._phase]
+
+    def current_result(self):
+        self.full = self._bufs[self._phase]
+        return self._results[self._phase] if self._results[self._phase] is not None else self.local_result()
 
     def gather(self, valid=None, summary=None, flags=None):
         """Completion handshake: when it has passed on this rank's stream, every rank's kernel of the step has finished

@@ -164,9 +164,11 @@ int fo_metric_stats(const FoMetricArgs *args, uint64_t *counters_dev, void *stre
  * device, runs fo_agents_pack + fo_metric_bundle, copies valid/summary/flags back and synchronises.
  * This is the call a non-torch embedder of the reference would make; device workspace is owned by
  * the library and grown on demand (per calling thread). `agents` holds HOST pointers here;
- * `out_pair` / `out_step` may be NULL. */
+ * `out_pair` / `out_step` may be NULL.  When `params->valid`, `->summary` and `->flags` are all non-NULL (and no detail
+ * output is requested) they are DEVICE buffers of n_traj rows in which the results are left as well -- a rank's slice of
+ * a gather buffer -- and `params->n_peers` / `peer_delta` apply as in fo_metric_bundle; otherwise they are ignored. */
 int fo_metric_bundle_host(const float *ego_host, int32_t n_traj, int32_t n_states, const FoAgentsRaw *agents_host,
-                          const FoMetricArgs *params /* vehicle, harm, dt, masks, thresholds are read */,
+                          const FoMetricArgs *params /* vehicle, harm, dt, masks, thresholds; optional device outputs */,
                           uint8_t *out_valid, float *out_summary, uint32_t *out_flags, float *out_pair,
                           float *out_step);
 
