@@ -776,7 +776,7 @@ static int launch_sweep_inst(const MetricKArgs& k, int num_sms, cudaStream_t st)
   // Float64 re-rounding of np.round(d, 3) ties is compiled into the variants that run when a clause of the validity mask
   // hangs on a rounded distance (dce / ttc / be thresholds armed, or the caller asked for it): there the mask is the
   // float64 reference's.  With those thresholds null (the deployment default, occlusion.yaml:20-28) only the last
-  // digit of the reported min_dce could differ, and the kernel without the tie path is 12 % faster.
+  // digit of the reported min_dce could differ, and the kernel without the tie path is a quarter faster.
   const bool ties = (k.tmask & (FO_T_DCE | FO_T_TTC | FO_T_BE)) != 0 || k.exact_dce;
   const bool uni = W == 1 && shape.lg_agents == 5;
   if (uni) return ties ? launch_sweep_shape<MASK, STATS, true, true>(k, num_sms, W, shape, st)
