@@ -45,6 +45,7 @@ constexpr int kSwMaxWarps = 8;
 #define FO_SW_TILE 128
 #endif
 constexpr int kSwTile = FO_SW_TILE;   // agents per tile (<= 256: 8-bit agent-in-tile field of the window items); bounds the per-team pair arrays
+static_assert(kSwTile <= 256, "agent-in-tile fields are 8 bits wide");
 constexpr int kSwQueue = 64;
 #ifndef FO_SW_MINB
 #define FO_SW_MINB 4
@@ -82,7 +83,7 @@ struct SweepSmem {
   uint32_t* colfirst;           // [kSwTile] first step with rounded distance 0
   uint32_t* q_near;             // [W][kSwQueue] (need LR4S << 31 | need box distance << 30 | agent-in-tile << 8 | step)
   uint32_t* q_cp;               // [W][kSwQueue] (agent-in-tile << 8 | step)
-  uint32_t* q_tie;              // [W][kSwQueue] (agent-in-tile << 8 | step): distances to re-round in float64
+  uint32_t* q_tie;              // [W][kSwQueue] (float32 rounding << 16 | agent-in-tile << 8 | step): distances to re-round in float64
   uint32_t* pool_near;          // [W * 32] leftovers of all warps
   uint32_t* pool_cp;            // [W * 32]
   float* red;                   // [W][16]
@@ -158,12 +159,25 @@ __device__ __forceinline__ void sw_harm_logits(const MetricKArgs& k, int model, 
 // np.round(d, 3) next to a x.xxx5 boundary (dce.py:79): queued candidates for the minimum are re-rounded from a float64
 // evaluation, 32 at a time with all lanes busy and out of line -- the float64 code (6 kB) and its call stay off the hot
 // path of the drains.  Returns the minimum of the re-rounded values; steps that round to 0 enter colfirst.
+// A queue entry carries the float32 rounding r of its distance ((r capped at 0xffff) << 16 | agent-in-tile << 8 | step).
+// The float64 value is r - 1, r or r + 1, so by the time the queue is drained an entry still matters only if it can be a
+// collision (r <= 1) or lie below the minimum found since (r <= rmin); when no lane holds such an entry the float64
+// code is not entered at all -- in a dense sweep the minimum is 0 after the first collision and the 6 kB stay out of the
+// instruction cache.
 static __device__ __noinline__ uint32_t sw_drain_ties(const MetricKArgs& k, const float4* egoA, const float2* egoB,
-                                                      uint32_t* colfirst, const uint32_t* src, int cnt, int a0, int lane) {
+                                                      uint32_t* colfirst, const uint32_t* src, int cnt, int a0, int lane,
+                                                      uint32_t rmin) {
   uint32_t r = 0xffffffu;
+  uint32_t item = 0u;
+  bool keep = false;
   if (lane < cnt) {
-    const uint32_t item = src[lane];
-    const int ial = (int)(item >> 8), ii = (int)(item & 0xffu);
+    item = src[lane];
+    const uint32_t rq = item >> 16;
+    keep = rq <= 1u || rq <= rmin;
+  }
+  if (!__any_sync(kFull, keep)) return r;
+  if (keep) {
+    const int ial = (int)((item >> 8) & 0xffu), ii = (int)(item & 0xffu);
     const int a = a0 + ial;
     const float4 s0 = __ldg(&k.tab.t0[(size_t)ii * k.tab.Ap + a]);
     const int4 pa = __ldg(reinterpret_cast<const int4*>(k.tab.prm + a));
@@ -342,10 +356,10 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         if (TIES) {
           const unsigned tb = __ballot_sync(kFull, tie);
           if (tb) {
-            if (tie) q_tie[qt + __popc(tb & lt_mask)] = item & 0xffffffu;
+            if (tie) q_tie[qt + __popc(tb & lt_mask)] = (item & 0xffffu) | (min(r - 1u, 0xffffu) << 16);   // r was bumped above
             qt += __popc(tb);
             __syncwarp();
-            if (qt >= 32) { qt -= 32; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, 32, a0, lane)); }
+            if (qt >= 32) { qt -= 32; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, 32, a0, lane, rmin)); }
           }
         }
         zb_e = fmaxf(zb_e, warp_max_signed(acc_ze));
@@ -563,7 +577,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
       }
       // ---- pool what is left in the per-warp queues across the team and drain it cooperatively --------------
       is_m1 = false;
-      if (TIES && UNI && qt > 0) { rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie, qt, a0, lane)); qt = 0; }
+      if (TIES && UNI && qt > 0) { rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie, qt, a0, lane, rmin)); qt = 0; }
       if (!UNI) {
         unsigned base_n = 0, base_c = 0;
         if (lane == 0) {
@@ -578,7 +592,7 @@ fo_metric_sweep_kernel(const __grid_constant__ MetricKArgs k, const SweepShape s
         const int tot_n = (int)w.scal[2], tot_c = (int)w.scal[3];
         for (int c = wib * 32; c < tot_n; c += 32 * W) drain_near(w.pool_near + c, min(32, tot_n - c));
         for (int c = wib * 32; c < tot_c; c += 32 * W) drain_cp(w.pool_cp + c, min(32, tot_c - c));
-        while (TIES && qt > 0) { const int c = min(qt, 32); qt -= c; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, c, a0, lane)); }
+        while (TIES && qt > 0) { const int c = min(qt, 32); qt -= c; rmin = min(rmin, sw_drain_ties(k, w.egoA, w.egoB, w.colfirst, q_tie + qt, c, a0, lane, rmin)); }
       }
       __syncthreads();                                 // pairkey / colfirst of the tile complete
       if (tid == 0) { w.scal[2] = 0u; w.scal[3] = 0u; }
