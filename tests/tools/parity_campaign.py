@@ -14,23 +14,30 @@ from frenetix_occlusion_b200 import synthetic as S  # noqa: E402
 from oracle import metric_oracle as MO  # noqa: E402
 import parity  # noqa: E402
 
-rng = np.random.default_rng(2024)
+rng = np.random.default_rng(int(os.environ.get("FO_CAMPAIGN_SEED", "2024")))     # FO_CAMPAIGN_SEED: another draw of bundles
 shapes = [(400, 32, 31), (150, 64, 51), (600, 6, 31), (80, 256, 51), (250, 20, 31), (1000, 3, 31)]
 agg = {"cases": 0, "pairs": 0, "trajectories": 0, "evaluations": 0, "hard_failures": [], "mask_mismatch": 0,
-       "ties_detail": {}, "ties_summary": {}, "ties_summary_one_warp_window_filter": {}, "cp_max_rel": 0.0}
+       "ties_detail": {}, "ties_summary": {}, "ties_summary_one_warp_window_filter": {}, "ties_summary_float64_tie_variant": {},
+       "cp_max_rel": 0.0}
 for rep_i in range(4):
     for (n, a, t) in shapes:
         seed = int(rng.integers(1, 1 << 30))
         case = S.make_case(n, a, t, seed=seed)
         out = MO.evaluate_bundle(case)
-        arms = [(True, "ties_detail", None), (False, "ties_summary", None)]
+        arms = [(True, "ties_detail", None, False), (False, "ties_summary", None, False)]
         if a >= 17:      # the throughput shape (one warp per trajectory, window filter); small bundles need it forced
-            arms.append((False, "ties_summary_one_warp_window_filter", "1"))
-        for detail, key, team in arms:
+            arms.append((False, "ties_summary_one_warp_window_filter", "1", False))
+        # the float64 tie variant of the summary kernel (FO_EXACT_DCE=1: what armed dce / ttc / be thresholds select)
+        arms.append((False, "ties_summary_float64_tie_variant", "1" if a >= 17 else None, True))
+        for detail, key, team, exact in arms:
             if team is None:
                 os.environ.pop("FO_TEAM_WARPS", None)
             else:
                 os.environ["FO_TEAM_WARPS"] = team
+            if exact:
+                os.environ["FO_EXACT_DCE"] = "1"
+            else:
+                os.environ.pop("FO_EXACT_DCE", None)
             res, _ = parity.run_gpu(case, want_pair=detail, want_step=detail)
             rep = parity.compare_bundle(out, res, case)
             for k, v in rep["ties"].items():
