@@ -95,9 +95,10 @@ def test_hot_kernels_stay_inside_the_instruction_cache_budget():
         hit = [v - cold.get(k, 0) for k, v in sizes.items() if all(p in k for p in parts)]
         assert len(hit) == 1, (parts, sorted(sizes))
         return hit[0]
-    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1ELb0E") <= 48 * 1024   # all 7 metrics, one-warp window-filter shape
+    # the throughput kernel sits at the edge of the instruction cache: +2-5 kB cost 5-8 % in every experiment
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1ELb0E") <= 44 * 1024   # all 7 metrics, one-warp window-filter shape
     assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb1ELb1E") <= 52 * 1024   # ... with the float64 tie path (armed dce / ttc / be)
-    assert size_of("fo_metric_sweep_kernel", "ILj111ELb0ELb1ELb0E") <= 40 * 1024   # default metrics (no BE)
-    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb0ELb0E") <= 60 * 1024   # team shape (latency path)
+    assert size_of("fo_metric_sweep_kernel", "ILj111ELb0ELb1ELb0E") <= 34 * 1024   # default metrics (no BE)
+    assert size_of("fo_metric_sweep_kernel", "ILj127ELb0ELb0ELb0E") <= 56 * 1024   # team shape (latency path)
     assert size_of("fo_metric_detail_kernel", "ILj127E") <= 50 * 1024            # detail kernel (lane = agent), all 7 metrics, incl. BE helpers
     assert size_of("fo_metric_detail_kernel", "ILj111E") <= 38 * 1024            # default metrics
