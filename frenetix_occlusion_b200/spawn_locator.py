@@ -73,6 +73,7 @@ class SpawnLocator:
         # sampling resolutions of this implementation
         self.raster_cell = 0.1        # m, occluded-area raster behind dynamic obstacles
         self.rect_cell = 0.025        # m, raster of the candidate phantom rectangles
+        self.path_refine = 1024       # subdivisions of the turn finder's 5 cm bracket around the path / occlusion crossing
         self.line_step = 0.01         # m, sampling of the lines perpendicular to the reference path
         self.path_step = 0.05         # m, sampling of the (shifted) reference path
 
@@ -442,18 +443,14 @@ class SpawnLocator:
         intersection = P[k]
         if k > 0:
             # the reference intersects the path with the occluded polygon exactly (spawn_locator.py:521-529): refine the
-            # 5 cm bracket [not occluded, occluded] with two more classified batches of 33 points -> 0.05 mm
+            # 5 cm bracket [not occluded, occluded] with ONE more classified batch of 1025 points -> 0.05 mm
             lo_s, hi_s = ss[k - 1], ss[k]
-            for _ in range(2):
-                cs = np.linspace(lo_s, hi_s, 33)
-                Pc = np.stack((np.interp(cs, cum, path[:, 0]), np.interp(cs, cum, path[:, 1])), -1)
-                oc = np.atleast_1d(self.sensor_model.occluded_area.contains(Pc))
-                oc[-1] = True
-                j = int(np.argmax(oc))
-                if j == 0:
-                    hi_s = lo_s
-                    break
-                lo_s, hi_s = cs[j - 1], cs[j]
+            cs = np.linspace(lo_s, hi_s, self.path_refine + 1)
+            Pc = np.stack((np.interp(cs, cum, path[:, 0]), np.interp(cs, cum, path[:, 1])), -1)
+            oc = np.atleast_1d(self.sensor_model.occluded_area.contains(Pc))
+            oc[-1] = True
+            j = int(np.argmax(oc))
+            hi_s = cs[j]
             intersection = np.array([np.interp(hi_s, cum, path[:, 0]), np.interp(hi_s, cum, path[:, 1])])
         s_intersection = self.cosy_cl.convert_to_curvilinear_coords(intersection[0], intersection[1])[0]
         s_phantom = s_intersection + self.phantom_offset_s[ego_intention]
