@@ -56,7 +56,10 @@ struct AgentTableView {
   int Ap;
 };
 
-constexpr int kWinSteps = 8;   // steps per window of the summary kernel's window filter
+#ifndef FO_WIN_STEPS
+#define FO_WIN_STEPS 8
+#endif
+constexpr int kWinSteps = FO_WIN_STEPS;   // steps per window of the summary kernel's window filter
 __host__ __device__ inline int agent_windows(int Tp) { return (Tp + kWinSteps - 1) / kWinSteps; }
 
 __host__ __device__ inline int agent_pad(int A) { return (A + 31) & ~31; }
