@@ -272,7 +272,10 @@ __device__ __forceinline__ float lr4s_coef(float ang, float side, float rear) {
 // into the kernel's dynamic shared memory, and the few kernel arguments they need travel by value: pointers and a
 // `const MetricKArgs&` would reach a noinline function as generic addresses (LD.E plus a uniform-register pair per access
 // instead of LDS / a register).
-constexpr int kBeBuckets = 64;   // arc-length -> state-index lookup used by the interpolation
+#ifndef FO_BE_BUCKETS
+#define FO_BE_BUCKETS 64
+#endif
+constexpr int kBeBuckets = FO_BE_BUCKETS;   // arc-length -> state-index lookup used by the interpolation
 struct BeView {
   uint32_t egoA;   // float4 [T] (x, y, cos theta, sin theta)
   uint32_t egoB;   // float2 [T] (theta, v)
