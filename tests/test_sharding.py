@@ -43,7 +43,10 @@ def _worker(rank, world, n_total, block, port, q):
 def test_two_rank_gather(n_total, block):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + n_total % 97
+    import socket
+    with socket.socket() as sock:                       # a free rendezvous port
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, n_total, block, port, q)) for r in range(2)]
     for p in procs:
         p.start()
